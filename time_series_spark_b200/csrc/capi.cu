@@ -1,0 +1,583 @@
+// C ABI of libprophet_b200.so (see include/prophet_b200.h).  Host-side orchestration only:
+// length classes, work queues, launches, staging copies.  All arithmetic is in the kernels.
+#define PB200_WITH_PREP 1
+#include "fit_kernel.cuh"
+#include "launch.h"
+#include "predict_kernel.cuh"
+#include "mc_kernel.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                      \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return fail(PB200_E_CUDA, #call, e_);  \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostBuf {   // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int NLC = 3;
+const int LC_NT[NLC] = {32, 64, 128};
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct pb200_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ctl_ev = nullptr;   // recorded after the H2D copies out of h_ctl
+    bool ctl_pending = false;
+    int64_t launches = 0;
+    // control workspace (device)
+    DevBuf d_offsets, d_order, d_lenclass, d_qitems, d_qctl;
+    HostBuf h_ctl;   // pinned staging for offsets / order / lenclass
+    // data staging for the *_host entry points
+    DevBuf d_ds, d_y, d_cap, d_params, d_tchange, d_mi32, d_mi64, d_mf64;
+    DevBuf d_fut, d_floor, d_yhat, d_lo, d_hi, d_yint;
+    DevBuf d_mc;     // MC workspace
+    int lc_max[NLC];
+};
+
+namespace {
+
+using pb200::FitArgs;
+using pb200::FitOptsDev;
+
+typedef cudaError_t (*launch_fn)(int, int, const FitArgs&, int, size_t, cudaStream_t, int*);
+const launch_fn LAUNCH[8] = {pb200::launch_fit_mask0, pb200::launch_fit_mask1, pb200::launch_fit_mask2,
+                             pb200::launch_fit_mask3, pb200::launch_fit_mask4, pb200::launch_fit_mask5,
+                             pb200::launch_fit_mask6, pb200::launch_fit_mask7};
+
+int check_opts(const pb200_options* o) {
+    if (!o) return fail(PB200_E_ARG, "options is null");
+    if (o->abi_version != PB200_ABI_VERSION) return fail(PB200_E_ARG, "options.abi_version mismatch");
+    if (o->growth != PB200_GROWTH_LINEAR && o->growth != PB200_GROWTH_LOGISTIC) return fail(PB200_E_ARG, "growth");
+    if (o->n_changepoints < 0 || o->n_changepoints > 30) return fail(PB200_E_UNSUPPORTED, "n_changepoints must be in [0, 30]");
+    if (o->history_size < 1 || o->history_size > pb200::HMAX) return fail(PB200_E_UNSUPPORTED, "history_size must be in [1, 5]");
+    if (!(o->changepoint_range > 0.0 && o->changepoint_range <= 1.0)) return fail(PB200_E_ARG, "changepoint_range");
+    if (!(o->changepoint_prior_scale > 0.0) || !(o->seasonality_prior_scale > 0.0)) return fail(PB200_E_ARG, "prior scales");
+    for (int v : {o->yearly, o->weekly, o->daily})
+        if (v != PB200_SEAS_AUTO && v != 0 && v != 1) return fail(PB200_E_UNSUPPORTED, "seasonality switch must be AUTO, 0 or 1");
+    if (o->max_iter < 1) return fail(PB200_E_ARG, "max_iter");
+    return PB200_OK;
+}
+
+FitOptsDev to_dev(const pb200_options* o) {
+    FitOptsDev d;
+    const double eps = 2.220446049250313e-16;
+    d.growth = o->growth;
+    d.mult = o->multiplicative ? 1 : 0;
+    d.n_changepoints = o->n_changepoints;
+    d.max_iter = o->max_iter;
+    d.history = o->history_size;
+    d.yearly = o->yearly;
+    d.weekly = o->weekly;
+    d.daily = o->daily;
+    d.changepoint_range = o->changepoint_range;
+    d.tau = o->changepoint_prior_scale;
+    d.seas_prior = o->seasonality_prior_scale;
+    d.init_alpha = o->init_alpha;
+    d.tol_obj = o->tol_obj;
+    d.tol_rel_obj_eps = o->tol_rel_obj * eps;
+    d.tol_grad = o->tol_grad;
+    d.tol_rel_grad_eps = o->tol_rel_grad * eps;
+    d.tol_param = o->tol_param;
+    return d;
+}
+
+int mask_nseas(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
+int mask_k(int m) { return ((m & 1) ? 20 : 0) + ((m & 2) ? 6 : 0) + ((m & 4) ? 8 : 0); }
+
+size_t y_elem(int dt) { return dt == PB200_Y_F64 ? 8 : 4; }
+
+}  // namespace
+
+extern "C" {
+
+PB200_API void pb200_default_options(pb200_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->abi_version = PB200_ABI_VERSION;
+    o->growth = PB200_GROWTH_LOGISTIC;       // prophet_modeler.py:65
+    o->multiplicative = 1;                   // prophet_modeler.py:65
+    o->n_changepoints = 25;
+    o->changepoint_range = 0.8;
+    o->changepoint_prior_scale = 0.05;
+    o->seasonality_prior_scale = 10.0;
+    o->yearly = o->weekly = o->daily = PB200_SEAS_AUTO;
+    o->max_iter = 10000;
+    o->history_size = 5;
+    o->init_alpha = 1e-3;
+    o->tol_obj = 1e-12;
+    o->tol_rel_obj = 1e4;
+    o->tol_grad = 1e-8;
+    o->tol_rel_grad = 1e7;
+    o->tol_param = 1e-8;
+    o->interval_width = 0.8;
+    o->uncertainty_samples = 1000;
+}
+
+PB200_API int pb200_get_layout(const pb200_options* o, pb200_layout* out) {
+    int rc = check_opts(o);
+    if (rc) return rc;
+    if (!out) return fail(PB200_E_ARG, "layout is null");
+    out->smax = o->n_changepoints > 0 ? o->n_changepoints : 1;
+    int k = 0;
+    if (o->yearly != 0) k += 20;
+    if (o->weekly != 0) k += 6;
+    if (o->daily != 0) k += 8;
+    out->kmax = k > 0 ? k : 1;
+    out->pstride = 3 + out->smax + out->kmax;
+    out->meta_i32_stride = 8;
+    out->meta_i64_stride = 2;
+    out->meta_f64_stride = 4;
+    return PB200_OK;
+}
+
+PB200_API const char* pb200_last_error(void) { return g_err.c_str(); }
+
+PB200_API pb200_ctx* pb200_create(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fail(PB200_E_CUDA, "no CUDA device (this library has no CPU path)", e);
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        fail(PB200_E_ARG, "device index out of range");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(PB200_E_CUDA, "cudaSetDevice");
+        return nullptr;
+    }
+    pb200_ctx* c = new pb200_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->sms = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        fail(PB200_E_CUDA, "device is not sm_100 (this library is compiled for sm_100a only)");
+        delete c;
+        return nullptr;
+    }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(PB200_E_CUDA, "cudaStreamCreate");
+        delete c;
+        return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&c->ctl_ev, cudaEventDisableTiming) != cudaSuccess) {
+        fail(PB200_E_CUDA, "cudaEventCreate");
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return nullptr;
+    }
+    c->lc_max[0] = env_int("PB200_LC0_MAX", 160);
+    c->lc_max[1] = env_int("PB200_LC1_MAX", 640);
+    c->lc_max[2] = 1 << 30;
+    return c;
+}
+
+PB200_API void pb200_destroy(pb200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->d_offsets, &c->d_order, &c->d_lenclass, &c->d_qitems, &c->d_qctl, &c->d_ds, &c->d_y, &c->d_cap,
+                      &c->d_params, &c->d_tchange, &c->d_mi32, &c->d_mi64, &c->d_mf64, &c->d_fut, &c->d_floor, &c->d_yhat,
+                      &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc})
+        b->release();
+    c->h_ctl.release();
+    cudaEventDestroy(c->ctl_ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+PB200_API void* pb200_stream(pb200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+PB200_API int64_t pb200_launch_count(pb200_ctx* c) { return c ? c->launches : 0; }
+
+PB200_API int pb200_synchronize(pb200_ctx* c) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return PB200_OK;
+}
+
+PB200_API int pb200_fit_device(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds, const void* d_y, int32_t y_dtype,
+                     const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
+                     const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
+                     int64_t* d_meta_i64, double* d_meta_f64) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (n_series < 0 || n_series > (1LL << 30)) return fail(PB200_E_ARG, "n_series");
+    if (n_series == 0) return PB200_OK;
+    if (!d_ds || !d_y || !h_offsets || !d_params || !d_tchange || !d_meta_i32 || !d_meta_i64 || !d_meta_f64)
+        return fail(PB200_E_ARG, "null pointer");
+    if (y_dtype < 0 || y_dtype > 2) return fail(PB200_E_ARG, "y_dtype");
+    pb200_layout L;
+    pb200_get_layout(opts, &L);
+    CK(cudaSetDevice(c->device));
+    const int N = (int)n_series;
+
+    // ---- host: length classes and longest-first order (counting sort on T) ----
+    size_t ctl_bytes = (size_t)(N + 1) * 8 + (size_t)N * 4 * 2;
+    if (c->ctl_pending) {   // the pinned staging of the previous call must have been consumed
+        CK(cudaEventSynchronize(c->ctl_ev));
+        c->ctl_pending = false;
+    }
+    CK(c->h_ctl.reserve(ctl_bytes));
+    int64_t* ho = (int64_t*)c->h_ctl.p;
+    int* horder = (int*)(ho + N + 1);
+    int* hlc = horder + N;
+    memcpy(ho, h_offsets, (size_t)(N + 1) * 8);
+    int lc_n[NLC] = {0, 0, 0}, lc_tmax[NLC] = {0, 0, 0};
+    int64_t tmax_all = 0;
+    for (int i = 0; i < N; ++i) {
+        const int64_t T = ho[i + 1] - ho[i];
+        if (T < 0) return fail(PB200_E_ARG, "offsets not monotone");
+        if (T > tmax_all) tmax_all = T;
+    }
+    if (tmax_all > (1 << 24)) return fail(PB200_E_UNSUPPORTED, "series longer than 2^24 rows");
+    {
+        std::vector<int> cnt((size_t)tmax_all + 2, 0);
+        for (int i = 0; i < N; ++i) cnt[(size_t)(ho[i + 1] - ho[i])]++;
+        // descending T: position of length t = number of series with length > t
+        std::vector<int> posv((size_t)tmax_all + 2, 0);
+        int acc = 0;
+        for (int64_t t = tmax_all; t >= 0; --t) { posv[(size_t)t] = acc; acc += cnt[(size_t)t]; }
+        for (int i = 0; i < N; ++i) {
+            const int T = (int)(ho[i + 1] - ho[i]);
+            horder[posv[(size_t)T]++] = i;
+            int lc = 0;
+            while (lc < NLC - 1 && T > c->lc_max[lc]) ++lc;
+            hlc[i] = lc;
+            lc_n[lc]++;
+            if (T > lc_tmax[lc]) lc_tmax[lc] = T;
+        }
+    }
+    // feasibility of the longest class in shared memory
+    const int nseas_max = (opts->yearly != 0) + (opts->weekly != 0) + (opts->daily != 0);
+    {
+        const int NT = LC_NT[NLC - 1];
+        const int chunk = (lc_tmax[NLC - 1] + NT - 1) / NT;
+        const size_t need = pb200::fit_smem_bytes(NT, nseas_max, chunk * NT, 64);
+        if (lc_n[NLC - 1] > 0 && need > 227 * 1024)
+            return fail(PB200_E_UNSUPPORTED, "series too long for the shared-memory-resident fit kernel");
+    }
+
+    // ---- device control buffers ----
+    CK(c->d_offsets.reserve((size_t)(N + 1) * 8));
+    CK(c->d_order.reserve((size_t)N * 4));
+    CK(c->d_lenclass.reserve((size_t)N * 4));
+    CK(c->d_qitems.reserve((size_t)NLC * 8 * N * 4));
+    CK(c->d_qctl.reserve((size_t)NLC * 8 * 2 * 4));
+    CK(cudaMemcpyAsync(c->d_offsets.p, ho, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_order.p, horder, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_lenclass.p, hlc, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ctl_ev, c->stream));
+    c->ctl_pending = true;
+    CK(cudaMemsetAsync(c->d_qctl.p, 0, (size_t)NLC * 8 * 2 * 4, c->stream));
+    CK(cudaMemsetAsync(d_params, 0, (size_t)N * L.pstride * 8, c->stream));
+    CK(cudaMemsetAsync(d_tchange, 0, (size_t)N * L.smax * 8, c->stream));
+    int* q_count = (int*)c->d_qctl.p;
+    int* q_head = q_count + NLC * 8;
+
+    const FitOptsDev od = to_dev(opts);
+    // ---- prep kernel ----
+    {
+        pb200::PrepArgs pa;
+        pa.ds = (const long long*)d_ds;
+        pa.y = d_y;
+        pa.y_dtype = y_dtype;
+        pa.offsets = (const long long*)c->d_offsets.p;
+        pa.order = (const int*)c->d_order.p;
+        pa.cap = d_cap;
+        pa.floor = floor;
+        pa.cap_multiplier = cap_multiplier;
+        pa.n_series = N;
+        pa.meta_i32 = d_meta_i32;
+        pa.meta_i64 = (long long*)d_meta_i64;
+        pa.meta_f64 = d_meta_f64;
+        pa.lenclass = (const int*)c->d_lenclass.p;
+        pa.q_items = (int*)c->d_qitems.p;
+        pa.q_count = q_count;
+        pa.o = od;
+        const int warps_per_block = 8;
+        int grid = (N + warps_per_block - 1) / warps_per_block;
+        grid = std::min(grid, c->sms * 8);
+        pb200::prep_kernel<<<grid, warps_per_block * 32, 0, c->stream>>>(pa);
+        CK(cudaGetLastError());
+        c->launches++;
+    }
+    // ---- fit kernels: one persistent launch per (length class, seasonality class) ----
+    for (int lc = 0; lc < NLC; ++lc) {
+        if (lc_n[lc] == 0) continue;
+        const int NT = LC_NT[lc];
+        const int chunk = (lc_tmax[lc] + NT - 1) / NT;
+        const int Tp = std::max(chunk, 1) * NT;
+        for (int mask = 0; mask < 8; ++mask) {
+            // seasonality classes that cannot occur under the options
+            auto impossible = [&](int bit, int sw) { return (sw == 0 && (mask & bit)) || (sw == 1 && !(mask & bit)); };
+            if (impossible(1, opts->yearly) || impossible(2, opts->weekly) || impossible(4, opts->daily)) continue;
+            const int K = mask_k(mask);
+            int ppad = L.smax + (K > 0 ? K : 1) + 3;
+            ppad = (ppad + 1) & ~1;
+            const size_t smem = pb200::fit_smem_bytes(NT, mask_nseas(mask), Tp, ppad);
+            if (smem > 227 * 1024) return fail(PB200_E_UNSUPPORTED, "series too long for shared memory");
+            FitArgs fa;
+            fa.ds = (const long long*)d_ds;
+            fa.y = d_y;
+            fa.y_dtype = y_dtype;
+            fa.offsets = (const long long*)c->d_offsets.p;
+            const int q = lc * 8 + mask;
+            fa.q_items = (const int*)c->d_qitems.p + (size_t)q * N;
+            fa.q_count = q_count + q;
+            fa.q_head = q_head + q;
+            fa.params = d_params;
+            fa.tchange = d_tchange;
+            fa.meta_i32 = d_meta_i32;
+            fa.meta_i64 = (long long*)d_meta_i64;
+            fa.meta_f64 = d_meta_f64;
+            fa.smax = L.smax;
+            fa.kmax = L.kmax;
+            fa.pstride = L.pstride;
+            fa.Tp = Tp;
+            fa.ppad = ppad;
+            fa.o = od;
+            int occ = 0;
+            CK(LAUNCH[mask](NT, opts->growth, fa, 0, smem, c->stream, &occ));
+            if (occ < 1) return fail(PB200_E_UNSUPPORTED, "fit kernel does not fit on an SM");
+            const int grid = (int)std::min<int64_t>((int64_t)lc_n[lc], (int64_t)c->sms * occ);
+            CK(LAUNCH[mask](NT, opts->growth, fa, grid, smem, c->stream, nullptr));
+            c->launches++;
+        }
+    }
+    return PB200_OK;
+}
+
+PB200_API int pb200_fit_host(pb200_ctx* c, const pb200_options* opts, const int64_t* h_ds, const void* h_y, int32_t y_dtype,
+                   const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier, const double* h_cap,
+                   double* h_params, double* h_tchange, int32_t* h_meta_i32, int64_t* h_meta_i64, double* h_meta_f64) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (n_series <= 0) return n_series == 0 ? PB200_OK : fail(PB200_E_ARG, "n_series");
+    if (!h_ds || !h_y || !h_offsets || !h_params || !h_tchange || !h_meta_i32 || !h_meta_i64 || !h_meta_f64)
+        return fail(PB200_E_ARG, "null pointer");
+    if (y_dtype < 0 || y_dtype > 2) return fail(PB200_E_ARG, "y_dtype");
+    pb200_layout L;
+    pb200_get_layout(opts, &L);
+    CK(cudaSetDevice(c->device));
+    const int64_t R = h_offsets[n_series];
+    const size_t N = (size_t)n_series;
+    CK(c->d_ds.reserve((size_t)R * 8));
+    CK(c->d_y.reserve((size_t)R * y_elem(y_dtype)));
+    CK(c->d_params.reserve(N * L.pstride * 8));
+    CK(c->d_tchange.reserve(N * L.smax * 8));
+    CK(c->d_mi32.reserve(N * 8 * 4));
+    CK(c->d_mi64.reserve(N * 2 * 8));
+    CK(c->d_mf64.reserve(N * 4 * 8));
+    CK(cudaMemcpyAsync(c->d_ds.p, h_ds, (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_y.p, h_y, (size_t)R * y_elem(y_dtype), cudaMemcpyHostToDevice, c->stream));
+    const double* dcap = nullptr;
+    if (h_cap) {
+        CK(c->d_cap.reserve(N * 8));
+        CK(cudaMemcpyAsync(c->d_cap.p, h_cap, N * 8, cudaMemcpyHostToDevice, c->stream));
+        dcap = (const double*)c->d_cap.p;
+    }
+    rc = pb200_fit_device(c, opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype, h_offsets, n_series, floor,
+                          cap_multiplier, dcap, (double*)c->d_params.p, (double*)c->d_tchange.p, (int32_t*)c->d_mi32.p,
+                          (int64_t*)c->d_mi64.p, (double*)c->d_mf64.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_params, c->d_params.p, N * L.pstride * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_tchange, c->d_tchange.p, N * L.smax * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_meta_i32, c->d_mi32.p, N * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_meta_i64, c->d_mi64.p, N * 2 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_meta_f64, c->d_mf64.p, N * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PB200_OK;
+}
+
+PB200_API int pb200_make_future_device(pb200_ctx* c, const int64_t* d_last_ds, int64_t n_models, int32_t horizon, int64_t freq_ns,
+                             int64_t* d_future_ds) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    if (n_models < 0 || horizon < 0) return fail(PB200_E_ARG, "sizes");
+    if (n_models == 0 || horizon == 0) return PB200_OK;
+    if (!d_last_ds || !d_future_ds) return fail(PB200_E_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    const int64_t n = n_models * horizon;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sms * 16);
+    pb200::make_future_kernel<<<grid, 256, 0, c->stream>>>((const long long*)d_last_ds, n_models, horizon, freq_ns,
+                                                           (long long*)d_future_ds);
+    CK(cudaGetLastError());
+    c->launches++;
+    return PB200_OK;
+}
+
+PB200_API int pb200_predict_device(pb200_ctx* c, const pb200_options* opts, const double* d_params, const double* d_tchange,
+                         const int32_t* d_meta_i32, const int64_t* d_meta_i64, const double* d_meta_f64,
+                         int64_t n_models, const int64_t* d_future_ds, int32_t horizon, const double* d_floor,
+                         const double* d_cap, uint64_t seed, double* d_yhat, double* d_yhat_lower, double* d_yhat_upper,
+                         int32_t* d_yhat_int) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (n_models < 0 || horizon < 0 || n_models > (1LL << 30)) return fail(PB200_E_ARG, "sizes");
+    if (n_models == 0 || horizon == 0) return PB200_OK;
+    if (!d_params || !d_tchange || !d_meta_i32 || !d_meta_i64 || !d_meta_f64 || !d_future_ds || !d_floor || !d_cap ||
+        !d_yhat || !d_yhat_int)
+        return fail(PB200_E_ARG, "null pointer");
+    pb200_layout L;
+    pb200_get_layout(opts, &L);
+    CK(cudaSetDevice(c->device));
+    pb200::PredictArgs a;
+    a.params = d_params;
+    a.tchange = d_tchange;
+    a.meta_i32 = d_meta_i32;
+    a.meta_i64 = (const long long*)d_meta_i64;
+    a.meta_f64 = d_meta_f64;
+    a.future_ds = (const long long*)d_future_ds;
+    a.floor = d_floor;
+    a.cap = d_cap;
+    a.n_models = (int)n_models;
+    a.horizon = horizon;
+    a.smax = L.smax;
+    a.kmax = L.kmax;
+    a.pstride = L.pstride;
+    a.growth = opts->growth;
+    a.mult = opts->multiplicative ? 1 : 0;
+    a.yhat = d_yhat;
+    a.trend = nullptr;
+    a.yhat_int = d_yhat_int;
+    {
+        dim3 grid((unsigned)n_models, (unsigned)std::min((horizon + 255) / 256, 64));
+        pb200::predict_kernel<<<grid, 256, 0, c->stream>>>(a);
+        CK(cudaGetLastError());
+        c->launches++;
+    }
+    if (d_yhat_lower && d_yhat_upper && opts->uncertainty_samples > 0) {
+        rc = pb200::launch_mc(c->stream, c->sms, a, opts->uncertainty_samples, opts->interval_width, seed, d_yhat_lower,
+                              d_yhat_upper);
+        if (rc == -1) return fail(PB200_E_UNSUPPORTED, "uncertainty_samples must be in [2, 1024]");
+        if (rc) return fail(PB200_E_CUDA, "mc kernel launch", cudaGetLastError());
+        c->launches++;
+    }
+    return PB200_OK;
+}
+
+PB200_API int pb200_predict_host(pb200_ctx* c, const pb200_options* opts, const double* h_params, const double* h_tchange,
+                       const int32_t* h_meta_i32, const int64_t* h_meta_i64, const double* h_meta_f64, int64_t n_models,
+                       const int64_t* h_future_ds, int32_t horizon, const double* h_floor, const double* h_cap,
+                       uint64_t seed, double* h_yhat, double* h_yhat_lower, double* h_yhat_upper, int32_t* h_yhat_int) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (n_models <= 0 || horizon <= 0) return (n_models == 0 || horizon == 0) ? PB200_OK : fail(PB200_E_ARG, "sizes");
+    if (!h_params || !h_tchange || !h_meta_i32 || !h_meta_i64 || !h_meta_f64 || !h_future_ds || !h_floor || !h_cap ||
+        !h_yhat || !h_yhat_int)
+        return fail(PB200_E_ARG, "null pointer");
+    pb200_layout L;
+    pb200_get_layout(opts, &L);
+    CK(cudaSetDevice(c->device));
+    const size_t N = (size_t)n_models, NH = N * (size_t)horizon;
+    const bool mc = h_yhat_lower && h_yhat_upper && opts->uncertainty_samples > 0;
+    CK(c->d_params.reserve(N * L.pstride * 8));
+    CK(c->d_tchange.reserve(N * L.smax * 8));
+    CK(c->d_mi32.reserve(N * 8 * 4));
+    CK(c->d_mi64.reserve(N * 2 * 8));
+    CK(c->d_mf64.reserve(N * 4 * 8));
+    CK(c->d_fut.reserve(NH * 8));
+    CK(c->d_floor.reserve(N * 8));
+    CK(c->d_cap.reserve(N * 8));
+    CK(c->d_yhat.reserve(NH * 8));
+    CK(c->d_yint.reserve(NH * 4));
+    if (mc) {
+        CK(c->d_lo.reserve(NH * 8));
+        CK(c->d_hi.reserve(NH * 8));
+    }
+    cudaStream_t st = c->stream;
+    CK(cudaMemcpyAsync(c->d_params.p, h_params, N * L.pstride * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_tchange.p, h_tchange, N * L.smax * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_mi32.p, h_meta_i32, N * 8 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_mi64.p, h_meta_i64, N * 2 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_mf64.p, h_meta_f64, N * 4 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_fut.p, h_future_ds, NH * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_floor.p, h_floor, N * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_cap.p, h_cap, N * 8, cudaMemcpyHostToDevice, st));
+    rc = pb200_predict_device(c, opts, (const double*)c->d_params.p, (const double*)c->d_tchange.p,
+                              (const int32_t*)c->d_mi32.p, (const int64_t*)c->d_mi64.p, (const double*)c->d_mf64.p,
+                              n_models, (const int64_t*)c->d_fut.p, horizon, (const double*)c->d_floor.p,
+                              (const double*)c->d_cap.p, seed, (double*)c->d_yhat.p, mc ? (double*)c->d_lo.p : nullptr,
+                              mc ? (double*)c->d_hi.p : nullptr, (int32_t*)c->d_yint.p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_yhat, c->d_yhat.p, NH * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_yhat_int, c->d_yint.p, NH * 4, cudaMemcpyDeviceToHost, st));
+    if (mc) {
+        CK(cudaMemcpyAsync(h_yhat_lower, c->d_lo.p, NH * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_yhat_upper, c->d_hi.p, NH * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return PB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// One translation unit per seasonality class (compile with -DPB200_MASK=0..7):
+// bit0 yearly (order 10), bit1 weekly (order 3), bit2 daily (order 4) -- the Fourier
+// orders Prophet.set_auto_seasonalities uses.  Instantiates fit_kernel for
+// NT in {32, 64, 128} x growth in {linear, logistic}.
+#include "fit_kernel.cuh"
+#include "launch.h"
+
+#ifndef PB200_MASK
+#error "compile with -DPB200_MASK=<0..7>"
+#endif
+
+namespace pb200 {
+
+constexpr int YO = (PB200_MASK & 1) ? 10 : 0;
+constexpr int WO = (PB200_MASK & 2) ? 3 : 0;
+constexpr int DO = (PB200_MASK & 4) ? 4 : 0;
+
+template <int NT, bool LOGI>
+static cudaError_t launch_one(const FitArgs& a, int grid, size_t smem, cudaStream_t st, int* occ) {
+    auto kern = fit_kernel<NT, LOGI, YO, WO, DO>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (occ) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, NT, smem);
+        return e;
+    }
+    kern<<<grid, NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+#define PB200_CAT_(a, b) a##b
+#define PB200_CAT(a, b) PB200_CAT_(a, b)
+
+cudaError_t PB200_CAT(launch_fit_mask, PB200_MASK)(int nt, int logi, const FitArgs& a, int grid, size_t smem,
+                                                   cudaStream_t st, int* occ) {
+    if (nt == 32) return logi ? launch_one<32, true>(a, grid, smem, st, occ) : launch_one<32, false>(a, grid, smem, st, occ);
+    if (nt == 64) return logi ? launch_one<64, true>(a, grid, smem, st, occ) : launch_one<64, false>(a, grid, smem, st, occ);
+    if (nt == 128) return logi ? launch_one<128, true>(a, grid, smem, st, occ) : launch_one<128, false>(a, grid, smem, st, occ);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace pb200
