@@ -169,6 +169,19 @@ PB200_API int pb200_fit_host(pb200_ctx* ctx, const pb200_options* opts,
                    int32_t* h_meta_i32, int64_t* h_meta_i64, double* h_meta_f64);
 
 /*
+ * Parity-test hook: evaluates the Prophet MAP objective (-log posterior up to constants,
+ * the function Stan's L-BFGS minimises) and its gradient at caller-supplied points, through
+ * the same kernel code the fit uses.  h_theta / h_grad rows have stride pstride and hold
+ * Stan's unconstrained order: k, m, delta[S_i], log(sigma_obs), beta[K_i] packed from 0.
+ * h_f[i] = objective, h_meta_i32 as in fit (status PB200_ST_INIT_ERROR when not finite).
+ */
+PB200_API int pb200_objective_host(pb200_ctx* ctx, const pb200_options* opts,
+                   const int64_t* h_ds, const void* h_y, int32_t y_dtype,
+                   const int64_t* h_offsets, int64_t n_series,
+                   double floor, double cap_multiplier, const double* h_theta,
+                   double* h_f, double* h_grad, int32_t* h_meta_i32);
+
+/*
  * Batched predict over `horizon` future timestamps per model.
  *   d_future_ds int64 ns [n_models * horizon]  (make_future_dataframe output,
  *               prophet_scorer.py:64-66; built by pb200_make_future_device or the caller)

@@ -1,0 +1,174 @@
+"""CPU tests of the drop-in boundary: the reference's plumbing contract (SURVEY.md section 4,
+ported from the reference's tests/unit/prophet_modeler_test.py and prophet_scorer_test.py
+minus Spark), the packer, the model-record wire format, and the C-ABI exports."""
+import ctypes
+import os
+import re
+from datetime import datetime
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from time_series_spark_b200 import _lib as L
+from time_series_spark_b200 import batched, model_record
+from time_series_spark_b200.frame import Frame
+from time_series_spark_b200.jobs.prophet_modeler import MODEL_INPUT_SCHEMA, ProphetModeler
+from time_series_spark_b200.jobs.prophet_scorer import ProphetScorer, extract_date, frequency_to_future
+from time_series_spark_b200.pack import pack_groups
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- reference tests/unit/prophet_modeler_test.py:52-56 -------------------------------------
+def test_read_dataframe(model_input_dir):
+    modeler = ProphetModeler({"io": {"input": model_input_dir, "models": "unused"},
+                              "model": {"floor": 0, "cap_multiplier": 1.1}})
+    spark_input_df = modeler.read_input_dataframe(None)
+    assert spark_input_df.columns == ["series_id", "dim_id", "ds", "y"]
+    assert spark_input_df.select("series_id").distinct().count() == 1
+    assert spark_input_df.select("dim_id").distinct().count() == 2
+    assert spark_input_df.count() == 816
+    assert [f.name for f in MODEL_INPUT_SCHEMA] == ["series_id", "dim_id", "start_time", "quantity"]
+    t = spark_input_df.table
+    assert t["series_id"].type == pa.int32() and t["y"].type == pa.int32() and pa.types.is_timestamp(t["ds"].type)
+    assert spark_input_df.filter("series_id = 751 and dim_id = 91").count() == 410
+
+
+# ---- reference tests/unit/prophet_scorer_test.py:55-80 --------------------------------------
+def test_convert_forecasts():
+    tbl = pa.table({"series_id": pa.array([101], pa.int32()), "dim_id": pa.array([66], pa.int32()),
+                    "ds": pa.array([datetime.strptime("2015-07-05 10:15:00", "%Y-%m-%d %H:%M:%S")], pa.timestamp("ns")),
+                    "yhat": pa.array([873242], pa.int32())})
+    output_df = ProphetScorer.convert_forecasts(Frame(tbl))
+    timestamp_regex = re.compile(r"^([0-9]{4})-(1[0-2]|0[1-9])-(3[01]|0[1-9]|[12][0-9])T"
+                                 r"(2[0-3]|[01][0-9]):([0-5][0-9]):([0-5][0-9])(\+00:00)$")
+    row = output_df.collect()[0]
+    assert timestamp_regex.match(row[0])
+    assert row[1] == 101
+    assert row[2] == 66
+    assert row[3] == "2015-07-05"
+    assert row[4] == datetime(2015, 7, 5, 10, 15)
+    assert row[5] == 873242
+    assert output_df.columns == ["created_timestamp", "series_id", "dim_id", "forecast_date",
+                                 "forecast_timestamp", "forecast_quantity"]
+    assert extract_date(datetime(2015, 7, 5, 10, 15)) == "2015-07-05"
+
+
+def test_write_forecasts_roundtrip(tmp_path):
+    import pyarrow.csv as pacsv
+    import pyarrow.dataset as pads
+    tbl = pa.table({"series_id": pa.array([1, 1], pa.int32()), "dim_id": pa.array([2, 2], pa.int32()),
+                    "ds": pa.array([0, 900 * 10**9], pa.int64()).cast(pa.timestamp("ns")),
+                    "yhat": pa.array([5, 6], pa.int32())})
+    scorer = ProphetScorer({"io": {"models": "unused", "forecasts": str(tmp_path / "forecasts")},
+                            "forecast": {"periods": 2, "frequency": "15min"}})
+    scorer.write_forecasts(scorer.convert_forecasts(Frame(tbl)))
+    scorer.write_forecasts(scorer.convert_forecasts(Frame(tbl)))      # mode='overwrite'
+    back = pads.dataset(str(tmp_path / "forecasts"), format="csv").to_table()
+    assert back.column_names == ["created_timestamp", "series_id", "dim_id", "forecast_date",
+                                 "forecast_timestamp", "forecast_quantity"]
+    assert back.num_rows == 2 and back["forecast_quantity"].to_pylist() == [5, 6]
+    assert back["forecast_date"].to_pylist()[0].strftime("%Y-%m-%d") == "1970-01-01" \
+        if not isinstance(back["forecast_date"][0].as_py(), str) else back["forecast_date"][0].as_py() == "1970-01-01"
+
+
+def test_pack_groups_sorts_groups_and_drops_null_y():
+    ns = 10**9
+    tbl = pa.table({
+        "series_id": pa.array([2, 1, 1, 1, 2, 1], pa.int32()),
+        "dim_id": pa.array([7, 5, 5, 5, 7, 9], pa.int32()),
+        "ds": pa.array([30 * ns, 20 * ns, 10 * ns, 40 * ns, 10 * ns, 5 * ns], pa.int64()).cast(pa.timestamp("ns")),
+        "y": pa.array([3, 2, 1, None, 4, 9], pa.int32()),
+    })
+    pk = pack_groups(tbl, pin=False)
+    assert pk.n == 3
+    assert pk.series_id.tolist() == [1, 1, 2] and pk.dim_id.tolist() == [5, 9, 7]
+    assert pk.offsets.tolist() == [0, 2, 3, 5]
+    assert pk.ds.tolist() == [10 * ns, 20 * ns, 5 * ns, 10 * ns, 30 * ns]
+    assert pk.y.tolist() == [1, 2, 9, 4, 3] and pk.y.dtype == np.int32
+    assert pk.last_ds.tolist() == [40 * ns, 5 * ns, 30 * ns]      # null-y row still anchors the future frame
+    assert pk.n_rows_in.tolist() == [3, 1, 2]
+    empty = pack_groups(tbl.slice(0, 0), pin=False)
+    assert empty.n == 0 and empty.offsets.tolist() == [0]
+
+
+def test_frame_subset():
+    f = Frame(pa.table({"a": [1, 1, 2], "b": [3, 3, 4]}))
+    assert f.count() == 3 and f.columns == ["a", "b"]
+    assert f.select("a").distinct().count() == 2
+    assert f.filter("a = 1 and b = 3").count() == 2
+    assert f.withColumnRenamed("a", "c").columns == ["c", "b"]
+    with pytest.raises(ValueError):
+        f.filter("a > 1")
+    with pytest.raises(TypeError):
+        f.groupby("a").apply(lambda t: t)
+
+
+def test_model_record_roundtrip():
+    opts = batched.make_options()
+    lay = L.get_layout(opts)
+    n = 5
+    rng = np.random.RandomState(0)
+    fb = batched.FittedBatch(rng.randn(n, lay.pstride), rng.randn(n, lay.smax),
+                             rng.randint(0, 100, (n, 8)).astype(np.int32), rng.randint(0, 10**15, (n, 2)).astype(np.int64),
+                             rng.randn(n, 4), lay.smax, lay.kmax)
+    last = rng.randint(0, 10**15, n).astype(np.int64)
+    col = model_record.encode(fb, last, opts)
+    assert len(col) == n and pa.types.is_binary(col.type)
+    tbl = pa.table({"model": col})
+    fb2, last2, info = model_record.decode(tbl["model"])
+    for a, b in ((fb.params, fb2.params), (fb.tchange, fb2.tchange), (fb.meta_i32, fb2.meta_i32),
+                 (fb.meta_i64, fb2.meta_i64), (fb.meta_f64, fb2.meta_f64), (last, last2)):
+        assert np.array_equal(a, b)
+    assert info == {"logistic": True, "multiplicative": True, "yearly": -1, "weekly": -1, "daily": -1,
+                    "n_changepoints": 25}
+    with pytest.raises(ValueError):
+        model_record.decode(pa.array([b"not a record, e.g. a pickle"], pa.binary()))
+
+
+def test_frequency_to_future_matches_pandas():
+    import pandas as pd
+    last = np.array([pd.Timestamp("2002-12-28 21:45:00").value, pd.Timestamp("2021-03-15 23:45:00").value])
+    for freq in ("15min", "H", "D", "W", "MS"):
+        fut = frequency_to_future(last, 5, freq)
+        for i, l in enumerate(last):
+            f = pd.offsets.Week() if freq == "W" else ("h" if freq == "H" else freq)   # 'W': prophet_scorer.py:59-62
+            ld = pd.Timestamp(int(l))
+            dates = pd.date_range(start=ld, periods=6, freq=f)
+            dates = dates[dates > ld][:5]
+            assert np.array_equal(fut[i], dates.values.astype("datetime64[ns]").astype(np.int64)), freq
+
+
+def test_make_options_defaults_are_the_reference_constructor():
+    o = batched.make_options()
+    assert (o.growth, o.multiplicative, o.n_changepoints) == (L.GROWTH_LOGISTIC, 1, 25)   # prophet_modeler.py:65
+    assert (o.yearly, o.weekly, o.daily) == (L.SEAS_AUTO,) * 3
+    assert (o.max_iter, o.history_size, o.init_alpha, o.tol_rel_grad) == (10000, 5, 1e-3, 1e7)
+    with pytest.raises(ValueError):
+        batched.make_options(yearly_seasonality=7)
+    with pytest.raises(ValueError):
+        batched.make_options(growth="flat")
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports everything include/prophet_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "prophet_b200.h")).read()
+    declared = sorted(set(re.findall(r"PB200_API[^;(]*?\b(pb200_\w+)\s*\(", hdr)))
+    assert declared == sorted(L.EXPORTS)
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    o = L.default_options()
+    lay = L.get_layout(o)
+    assert (lay.smax, lay.kmax, lay.pstride) == (25, 34, 62)
+    assert ctypes.sizeof(L.Options) == 128
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """On a box without CUDA the product path fails loudly instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(L.Pb200Error):
+        L.Context(0)

@@ -1,0 +1,73 @@
+"""GPU end-to-end tests of the drop-in jobs: the reference's own test flow
+(tests/unit/prophet_modeler_test.py:59-75, tests/unit/prophet_scorer_test.py:83-114) with Spark
+replaced by the batched operators, on the reference's fixture (config #1)."""
+import numpy as np
+import pyarrow.dataset as pads
+import pytest
+
+from time_series_spark_b200.jobs.prophet_modeler import ProphetModeler, model_time_series
+from time_series_spark_b200.jobs.prophet_scorer import ProphetScorer, forecast_time_series
+
+pytestmark = pytest.mark.gpu
+
+
+def test_model_then_forecast_time_series(tmp_path, model_input_dir, golden_oracle):
+    mconfig = {"io": {"input": model_input_dir, "models": str(tmp_path / "build" / "models")},
+               "model": {"floor": 0, "cap_multiplier": 1.1}}
+    modeler = ProphetModeler(mconfig)
+    spark_input_df = modeler.read_input_dataframe(None)
+    # ---- test_model_time_series ----
+    output_df = spark_input_df.groupby("series_id", "dim_id").apply(model_time_series(modeler.config))
+    assert output_df.count() == 2
+    assert output_df.columns == ["series_id", "dim_id", "floor", "cap", "model"]
+    assert output_df.filter("series_id = 751 and dim_id = 91").count() == 1
+    assert output_df.filter("series_id = 751 and dim_id = 155").count() == 1
+    caps = dict(zip(output_df.table["dim_id"].to_pylist(), output_df.table["cap"].to_pylist()))
+    assert caps[91] == np.float32(103591.40000000001) and caps[155] == np.float32(140054.2)   # FloatType column
+    modeler.persist_models(output_df)
+    model_df = pads.dataset(mconfig["io"]["models"], format="parquet").to_table()
+    assert model_df.num_rows == 2
+    assert model_df.column_names == ["series_id", "dim_id", "floor", "cap", "model"]
+
+    # ---- test_read_model_dataframe / test_forecast_time_series ----
+    sconfig = {"io": {"models": mconfig["io"]["models"], "forecasts": str(tmp_path / "build" / "forecasts")},
+               "forecast": {"periods": 40, "frequency": "15min"}}
+    scorer = ProphetScorer(sconfig)
+    spark_model_df = scorer.read_model_dataframe(None)
+    assert spark_model_df.columns == ["series_id", "dim_id", "floor", "cap", "model"]
+    assert spark_model_df.select("series_id").distinct().count() == 1
+    assert spark_model_df.select("dim_id").distinct().count() == 2
+    assert spark_model_df.count() == 2
+    output_df = spark_model_df.groupby("series_id", "dim_id").apply(forecast_time_series(scorer.config))
+    assert output_df.count() == 80
+    assert output_df.columns == ["series_id", "dim_id", "ds", "yhat"]
+    assert output_df.filter("series_id = 751 and dim_id = 91").count() == 40
+    assert output_df.filter("series_id = 751 and dim_id = 155").count() == 40
+    # numerical contract the reference never asserted: forecast close to the oracle's golden vector
+    for dim in (91, 155):
+        sub = output_df.filter(f"series_id = 751 and dim_id = {dim}").table
+        got = np.asarray(sub["yhat"].to_pylist(), dtype=np.float64)
+        ts = np.asarray(sub["ds"].cast("int64").to_pylist(), dtype=np.int64)
+        assert np.array_equal(ts, golden_oracle[f"d{dim}_future_ns"])
+        ys = float(golden_oracle[f"d{dim}_y_scale"])
+        assert np.max(np.abs(got - golden_oracle[f"d{dim}_yhat_int"])) <= 3e-2 * ys + 1
+    converted_df = scorer.convert_forecasts(output_df)
+    scorer.write_forecasts(converted_df)
+    read_output_df = pads.dataset(sconfig["io"]["forecasts"], format="csv").to_table()
+    assert read_output_df.column_names == ["created_timestamp", "series_id", "dim_id", "forecast_date",
+                                           "forecast_timestamp", "forecast_quantity"]
+    assert read_output_df.num_rows == 80
+
+
+def test_static_entry_points_and_intervals(tmp_path, model_input_dir):
+    mconfig = {"io": {"input": model_input_dir, "models": str(tmp_path / "models")},
+               "model": {"floor": 0, "cap_multiplier": 1.1}}
+    ProphetModeler.model(None, mconfig)
+    sconfig = {"io": {"models": mconfig["io"]["models"], "forecasts": str(tmp_path / "forecasts")},
+               "forecast": {"periods": 8, "frequency": "W", "intervals": True, "seed": 5}}
+    ProphetScorer.score(None, sconfig)
+    out = pads.dataset(sconfig["io"]["forecasts"], format="csv").to_table()
+    assert out.num_rows == 16
+    assert out.column_names[-2:] == ["yhat_lower", "yhat_upper"]
+    lo, hi, q = (np.asarray(out[c].to_pylist(), dtype=float) for c in ("yhat_lower", "yhat_upper", "forecast_quantity"))
+    assert np.all(lo < hi) and np.all(q >= 0)

@@ -1,0 +1,269 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI
+(libprophet_b200.so via ctypes); the numpy oracle is only the checker.
+
+What can and cannot be pinned.  The model arithmetic (objective, gradient, predict) is
+checked to ~1e-10 relative.  The FITTED parameters are the end point of Stan's L-BFGS with
+its loose relative-gradient stop (1e7 * eps) on a non-smooth objective (Laplace prior): the
+trajectory amplifies last-bit differences, so two correct fp64 implementations with different
+summation order agree bit-for-bit on many series and drift apart on others.  The oracle
+shows the same spread against ITSELF when one input is perturbed by one ulp
+(test_fit_discrepancy_is_at_the_algorithms_own_sensitivity), so the stated tolerances for
+fitted values are distribution-level: forecast differences relative to y_scale.
+Stated tolerances (FP, relative to y_scale unless noted):
+  objective value at a given point      1e-10 relative
+  gradient at a given point             1e-8  relative to max(1, |g|_inf)
+  predict given identical parameters    1e-12
+  fitted forecast vs oracle             median <= 2e-3, max <= 3e-2   (config 2/3/4 samples)
+  objective at the returned optimum     |f_gpu - f_oracle| <= 2e-3 * |f|
+  MC interval bounds                    within 0.05 sigma_obs*y_scale of the oracle's own 1000-draw bounds (mean)
+"""
+import numpy as np
+import pytest
+
+from oracle import prophet_oracle as po
+from time_series_spark_b200 import _lib as L
+from time_series_spark_b200 import batched, synth
+
+pytestmark = pytest.mark.gpu
+
+NS15 = 15 * 60 * 10**9
+
+
+def _cases():
+    return [
+        ("c3", synth.config3(n=24), batched.make_options(), po.ProphetOptions(), NS15),
+        ("c2", synth.config2(n=24), batched.make_options(growth="linear", yearly_seasonality=True),
+         po.ProphetOptions(growth="linear", yearly_seasonality=True), 86400 * 10**9),
+        ("c2_additive_logistic", synth.config2(n=12),
+         batched.make_options(growth="logistic", seasonality_mode="additive", yearly_seasonality=True),
+         po.ProphetOptions(growth="logistic", seasonality_mode="additive", yearly_seasonality=True), 86400 * 10**9),
+        ("c4", synth.config4(n=48), batched.make_options(), po.ProphetOptions(), NS15),
+    ]
+
+
+def _fixture_batch(gi):
+    order = np.lexsort((gi["ds_ns"], gi["dim_id"]))
+    dim, ds, y = gi["dim_id"][order], gi["ds_ns"][order], gi["y"][order]
+    cut = int(np.searchsorted(dim, 155))
+    return synth.RaggedBatch(np.array([751, 751], np.int32), np.array([91, 155], np.int32),
+                             np.array([0, cut, dim.size], np.int64), np.ascontiguousarray(ds),
+                             np.ascontiguousarray(y.astype(np.int32)))
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
+def test_objective_and_gradient_match_oracle(gpu_ctx, case):
+    name, b, opts, oopts, _ = case
+    lay = L.get_layout(opts)
+    rng = np.random.RandomState(11)
+    thetas, preps = [], []
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        y = b.y[a:e].astype(np.float64)
+        p = po.prepare(b.ds[a:e], y, 0.0, y.max() * 1.1, oopts)
+        th = po.initial_theta(p) + 0.05 * rng.randn(p.S + p.K + 3)
+        row = np.zeros(lay.pstride)
+        row[:th.size] = th
+        thetas.append(row)
+        preps.append((p, th))
+    f, g, mi = batched.objective_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1, np.array(thetas))
+    for i, (p, th) in enumerate(preps):
+        err, fo, go = po.neg_logp_grad(th, p)
+        assert err == 0 and mi[i, 4] == 0
+        assert (mi[i, 0], mi[i, 1]) == (p.T, p.S)
+        assert abs(f[i] - fo) <= 1e-10 * max(1.0, abs(fo)), (name, i, f[i], fo)
+        gd = np.max(np.abs(g[i, :th.size] - go)) / max(1.0, np.max(np.abs(go)))
+        assert gd <= 1e-8, (name, i, gd)
+
+
+def test_objective_on_reference_fixture_matches_golden(gpu_ctx, golden_input, golden_oracle):
+    """Config #1 input (the reference's only fixture): objective/gradient at the golden points."""
+    b = _fixture_batch(golden_input)
+    opts = batched.make_options()
+    lay = L.get_layout(opts)
+    for j in range(4):
+        th = np.zeros((2, lay.pstride))
+        for i, dim in enumerate((91, 155)):
+            pt = golden_oracle[f"d{dim}_points"][j]
+            th[i, :pt.size] = pt
+        f, g, mi = batched.objective_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1, th)
+        for i, dim in enumerate((91, 155)):
+            fo, go = golden_oracle[f"d{dim}_f"][j], golden_oracle[f"d{dim}_g"][j]
+            assert abs(f[i] - fo) <= 1e-10 * abs(fo)
+            assert np.max(np.abs(g[i, :go.size] - go)) <= 1e-8 * max(1.0, np.max(np.abs(go)))
+            assert mi[i, 3] == 6          # weekly + daily, yearly off (span 722.4 d < 730 d)
+
+
+def test_fit_reference_fixture(gpu_ctx, golden_input, golden_oracle):
+    b = _fixture_batch(golden_input)
+    opts = batched.make_options()
+    fb = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    for i, dim in enumerate((91, 155)):
+        k = f"d{dim}_"
+        assert fb.meta_i32[i, 4] in (L.ST_RELGRAD, L.ST_RELF, L.ST_ABSX)
+        assert fb.meta_f64[i, 0] == float(golden_oracle[k + "y_scale"])
+        assert fb.meta_f64[i, 2] == float(golden_oracle[k + "cap"])          # cap in double, prophet_modeler.py:59
+        assert np.array_equal(fb.tchange[i], golden_oracle[k + "t_change"])
+        fo = float(golden_oracle[k + "neg_logp"])
+        assert abs(fb.meta_f64[i, 3] - fo) <= 2e-3 * abs(fo)
+        fut = golden_oracle[k + "future_ns"][None, :]
+        one = batched.FittedBatch(fb.params[i:i + 1], fb.tchange[i:i + 1], fb.meta_i32[i:i + 1],
+                                  fb.meta_i64[i:i + 1], fb.meta_f64[i:i + 1], fb.smax, fb.kmax)
+        fc = batched.predict_batch_host(gpu_ctx, opts, one, fut, np.zeros(1), np.array([float(golden_oracle[k + "cap32"])]),
+                                        intervals=False)
+        rel = np.max(np.abs(fc.yhat[0] - golden_oracle[k + "yhat_future"])) / float(golden_oracle[k + "y_scale"])
+        assert rel <= 3e-2, (dim, rel)
+        assert np.max(np.abs(fc.yhat_int[0] - golden_oracle[k + "yhat_int"])) <= 3e-2 * float(golden_oracle[k + "y_scale"]) + 1
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
+def test_fit_and_forecast_match_oracle_within_stated_tolerance(gpu_ctx, case):
+    name, b, opts, oopts, freq = case
+    fb = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    last = b.ds[b.offsets[1:] - 1]
+    fut = batched.make_future(last, 48, freq)
+    cap32 = fb.meta_f64[:, 2].astype(np.float32).astype(np.float64)
+    fc = batched.predict_batch_host(gpu_ctx, opts, fb, fut, np.zeros(b.n), cap32, intervals=False)
+    rel, same_path = [], 0
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        fr = po.fit(b.ds[a:e], b.y[a:e].astype(np.float64), opts=oopts)
+        assert fb.meta_i32[i, 4] >= 0 and fr.ret >= 0
+        S, K = fr.prep.S, fr.prep.K
+        assert (fb.meta_i32[i, 0], fb.meta_i32[i, 1]) == (fr.prep.T, S)
+        assert np.array_equal(fb.tchange[i, :S], fr.prep.t_change)
+        assert abs(fb.meta_f64[i, 3] - fr.neg_logp) <= 2e-3 * abs(fr.neg_logp), (name, i)
+        pr = po.predict(fr, fut[i], 0.0, cap32[i], oopts)
+        rel.append(np.max(np.abs(pr["yhat"] - fc.yhat[i])) / fr.prep.y_scale)
+        if fb.meta_i32[i, 5] == fr.iters and fb.meta_i32[i, 6] == fr.n_evals:
+            # identical optimiser trajectory: parameters agree to rounding amplification only
+            same_path += 1
+            assert abs(fb.params[i, 0] - fr.k) < 1e-5 and abs(fb.params[i, 1] - fr.m) < 1e-5
+            assert np.max(np.abs(fb.params[i, 3:3 + S] - fr.delta)) < 1e-5
+            if fr.prep.seasonalities:
+                assert np.max(np.abs(fb.params[i, 3 + fb.smax:3 + fb.smax + K] - fr.beta)) < 1e-5
+    rel = np.array(rel)
+    assert np.median(rel) <= 2e-3 and rel.max() <= 3e-2, (name, np.median(rel), rel.max())
+    if name == "c4":
+        assert same_path >= b.n // 4     # short series mostly follow the oracle's exact iteration path
+
+
+def test_fit_discrepancy_is_at_the_algorithms_own_sensitivity(gpu_ctx):
+    """GPU-vs-oracle forecast spread is no larger than oracle-vs-oracle when ONE input value is
+    moved by one ulp: the difference is the algorithm's conditioning, not an implementation error."""
+    b = synth.config3(n=16)
+    opts, oopts = batched.make_options(), po.ProphetOptions()
+    fb = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    last = b.ds[b.offsets[1:] - 1]
+    fut = batched.make_future(last, 48, NS15)
+    cap32 = fb.meta_f64[:, 2].astype(np.float32).astype(np.float64)
+    fc = batched.predict_batch_host(gpu_ctx, opts, fb, fut, np.zeros(b.n), cap32, intervals=False)
+    d_gpu, d_self = [], []
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        ds, y = b.ds[a:e], b.y[a:e].astype(np.float64)
+        fr = po.fit(ds, y, opts=oopts)
+        pr = po.predict(fr, fut[i], 0.0, cap32[i], oopts)
+        y2 = y.copy()
+        y2[y2.size // 2] = np.nextafter(y2[y2.size // 2], np.inf)
+        pr2 = po.predict(po.fit(ds, y2, opts=oopts), fut[i], 0.0, cap32[i], oopts)
+        d_gpu.append(np.max(np.abs(pr["yhat"] - fc.yhat[i])) / fr.prep.y_scale)
+        d_self.append(np.max(np.abs(pr["yhat"] - pr2["yhat"])) / fr.prep.y_scale)
+    assert np.median(d_gpu) <= 5 * np.median(d_self) + 1e-6
+    assert np.max(d_gpu) <= 10 * np.max(d_self) + 1e-6
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
+def test_predict_kernel_matches_oracle_given_same_parameters(gpu_ctx, case):
+    name, b, opts, oopts, freq = case
+    fb = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    last = b.ds[b.offsets[1:] - 1]
+    fut = batched.make_future(last, 40, freq)
+    cap32 = fb.meta_f64[:, 2].astype(np.float32).astype(np.float64)
+    fc = batched.predict_batch_host(gpu_ctx, opts, fb, fut, np.zeros(b.n), cap32, intervals=False)
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        y = b.y[a:e].astype(np.float64)
+        p = po.prepare(b.ds[a:e], y, 0.0, y.max() * 1.1, oopts)
+        S, K = p.S, p.K
+        fr = po.FitResult(prep=p, k=fb.params[i, 0], m=fb.params[i, 1], delta=fb.params[i, 3:3 + S].copy(),
+                          sigma_obs=fb.params[i, 2], beta=fb.params[i, 3 + fb.smax:3 + fb.smax + K].copy(),
+                          theta=None, neg_logp=0.0, iters=0, n_evals=0, ret=0)
+        pr = po.predict(fr, fut[i], 0.0, cap32[i], oopts)
+        assert np.max(np.abs(pr["yhat"] - fc.yhat[i])) <= 1e-12 * p.y_scale * max(1.0, np.max(np.abs(pr["yhat"])) / p.y_scale)
+        exp_int = po.scorer_epilogue(pr["yhat"], 0.0)
+        assert np.sum(exp_int != fc.yhat_int[i]) == 0 or np.max(np.abs(exp_int - fc.yhat_int[i])) <= 1
+
+
+def test_mc_intervals_statistically_match_oracle(gpu_ctx):
+    b = synth.config3(n=4)
+    opts, oopts = batched.make_options(), po.ProphetOptions()
+    fb = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    last = b.ds[b.offsets[1:] - 1]
+    fut = batched.make_future(last, 96, NS15)
+    cap32 = fb.meta_f64[:, 2].astype(np.float32).astype(np.float64)
+    fc = batched.predict_batch_host(gpu_ctx, opts, fb, fut, np.zeros(b.n), cap32, seed=7, intervals=True)
+    fc2 = batched.predict_batch_host(gpu_ctx, opts, fb, fut, np.zeros(b.n), cap32, seed=7, intervals=True)
+    assert np.array_equal(fc.yhat_lower, fc2.yhat_lower) and np.array_equal(fc.yhat_upper, fc2.yhat_upper)
+    assert np.all(fc.yhat_lower < fc.yhat) and np.all(fc.yhat < fc.yhat_upper)
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        y = b.y[a:e].astype(np.float64)
+        p = po.prepare(b.ds[a:e], y, 0.0, y.max() * 1.1, oopts)
+        S, K = p.S, p.K
+        fr = po.FitResult(prep=p, k=fb.params[i, 0], m=fb.params[i, 1], delta=fb.params[i, 3:3 + S].copy(),
+                          sigma_obs=fb.params[i, 2], beta=fb.params[i, 3 + fb.smax:3 + fb.smax + K].copy(),
+                          theta=None, neg_logp=0.0, iters=0, n_evals=0, ret=0)
+        pr = po.predict(fr, fut[i], 0.0, cap32[i], oopts)
+        un = po.predict_uncertainty(fr, fut[i], pr, np.random.RandomState(3), oopts)
+        sd = fr.sigma_obs * p.y_scale
+        assert abs(np.mean(fc.yhat_lower[i] - un["yhat_lower"])) <= 0.05 * sd
+        assert abs(np.mean(fc.yhat_upper[i] - un["yhat_upper"])) <= 0.05 * sd
+        # pointwise: MC standard error of a 10 % quantile from 1000 draws is ~0.055 sd
+        assert np.max(np.abs(fc.yhat_lower[i] - un["yhat_lower"])) <= 0.4 * sd
+        width_o = np.mean(un["yhat_upper"] - un["yhat_lower"])
+        assert abs(np.mean(fc.yhat_upper[i] - fc.yhat_lower[i]) - width_o) <= 0.03 * width_o
+
+
+def test_scale_equivariance_and_batch_independence(gpu_ctx):
+    """Size-independent properties: y -> 2y leaves every scaled quantity bit-identical
+    (y_scale absorbs it); a series' result does not depend on what else is in the batch."""
+    b = synth.config3(n=64)
+    opts = batched.make_options()
+    fb = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    fb2 = batched.fit_batch_host(gpu_ctx, opts, b.ds, (b.y * 2).astype(np.int32), b.offsets, 0.0, 1.1)
+    assert np.array_equal(fb.params, fb2.params)
+    assert np.array_equal(fb2.meta_f64[:, 0], 2 * fb.meta_f64[:, 0])
+    sub = b.take(10, 20)
+    fb3 = batched.fit_batch_host(gpu_ctx, opts, sub.ds, sub.y, sub.offsets, 0.0, 1.1)
+    assert np.array_equal(fb3.params, fb.params[10:20]) and np.array_equal(fb3.meta_i32[:, 4:7], fb.meta_i32[10:20, 4:7])
+    # f64 / f32 input dtypes give the same fit as int32
+    fb4 = batched.fit_batch_host(gpu_ctx, opts, sub.ds, sub.y.astype(np.float64), sub.offsets, 0.0, 1.1)
+    assert np.array_equal(fb4.params, fb3.params)
+
+
+def test_edge_cases_status_codes(gpu_ctx):
+    ns = 10**9
+    day = 86400 * ns
+    ds = np.concatenate([np.arange(1) * day, np.arange(2) * day, np.arange(30) * day, np.arange(30) * day,
+                         np.arange(30) * day]).astype(np.int64)
+    y = np.concatenate([[5], [3, 4], np.full(30, 7), np.arange(30) + 1, np.zeros(30)]).astype(np.int32)
+    offsets = np.array([0, 1, 3, 33, 63, 93], np.int64)
+    # logistic (reference default): 1 row -> TOO_FEW; all-zero y -> cap = 0 <= floor -> CAP_LE_FLOOR
+    fb = batched.fit_batch_host(gpu_ctx, batched.make_options(), ds, y, offsets, 0.0, 1.1)
+    st = fb.meta_i32[:, 4]
+    assert st[0] == L.ST_TOO_FEW and st[4] == L.ST_CAP_LE_FLOOR
+    assert st[1] >= 0 or st[1] in (L.ST_LSFAIL, L.ST_INIT_ERROR)      # 2 rows: S = 1 dummy changepoint
+    assert st[3] >= 0
+    # linear growth, constant y: fbprophet's "nothing to fit" shortcut
+    fl = batched.fit_batch_host(gpu_ctx, batched.make_options(growth="linear"), ds, y, offsets, 0.0, 1.1)
+    assert fl.meta_i32[2, 4] == L.ST_CONST_LINEAR and fl.params[2, 2] == 1e-9
+    fr = po.fit(ds[3:33], y[3:33].astype(float), opts=po.ProphetOptions(growth="linear"))
+    assert abs(fl.params[2, 0] - fr.k) < 1e-12 and abs(fl.params[2, 1] - fr.m) < 1e-12
+    # empty batch
+    e = batched.fit_batch_host(gpu_ctx, batched.make_options(), ds[:0], y[:0], np.zeros(1, np.int64), 0.0, 1.1)
+    assert e.n == 0
+    # unsorted timestamps are rejected per series, not silently fitted
+    ds_bad = ds.copy()
+    ds_bad[40], ds_bad[41] = ds_bad[41], ds_bad[40]
+    fbad = batched.fit_batch_host(gpu_ctx, batched.make_options(), ds_bad, y, offsets, 0.0, 1.1)
+    assert fbad.meta_i32[3, 4] == L.ST_BAD_INPUT

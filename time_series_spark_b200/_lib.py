@@ -44,7 +44,7 @@ class Layout(C.Structure):
 EXPORTS = [
     "pb200_default_options", "pb200_get_layout", "pb200_create", "pb200_destroy", "pb200_last_error",
     "pb200_stream", "pb200_launch_count", "pb200_fit_device", "pb200_fit_host", "pb200_predict_device",
-    "pb200_predict_host", "pb200_make_future_device", "pb200_synchronize",
+    "pb200_predict_host", "pb200_make_future_device", "pb200_synchronize", "pb200_objective_host",
 ]
 
 _lib = None
@@ -88,6 +88,8 @@ def load() -> C.CDLL:
     lib.pb200_predict_host.restype = C.c_int
     lib.pb200_make_future_device.argtypes = [vp, vp, i64, i32, i64, vp]
     lib.pb200_make_future_device.restype = C.c_int
+    lib.pb200_objective_host.argtypes = [vp, OP, vp, vp, i32, vp, i64, dbl, dbl, vp, vp, vp, vp]
+    lib.pb200_objective_host.restype = C.c_int
     lib.pb200_synchronize.argtypes = [vp]
     lib.pb200_synchronize.restype = C.c_int
     _lib = lib

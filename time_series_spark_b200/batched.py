@@ -218,3 +218,24 @@ def predict_batch_device(ctx: L.Context, opts: L.Options, fitted: FittedBatch, f
         if sync:
             ctx.synchronize()
     return ForecastBatch(future_ds, yhat, lo, hi, yint)
+
+
+def objective_host(ctx: L.Context, opts: L.Options, ds_ns: np.ndarray, y: np.ndarray, offsets: np.ndarray,
+                   floor: float, cap_multiplier: float, theta: np.ndarray):
+    """pb200_objective_host (parity-test hook): objective and gradient at ``theta`` rows
+    (Stan unconstrained order k, m, delta[S], log sigma, beta[K], zero-padded to pstride)."""
+    ds_ns = np.ascontiguousarray(ds_ns, dtype=np.int64)
+    y = np.ascontiguousarray(y)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    lay = L.get_layout(opts)
+    th = np.zeros((n, lay.pstride), np.float64)
+    th[:, :theta.shape[1]] = theta
+    f = np.empty(n, np.float64)
+    g = np.empty((n, lay.pstride), np.float64)
+    mi32 = np.empty((n, 8), np.int32)
+    rc = L.load().pb200_objective_host(ctx.handle, C.byref(opts), _np_ptr(ds_ns), _np_ptr(y), _y_dtype(y),
+                                       _np_ptr(offsets), n, float(floor), float(cap_multiplier), _np_ptr(th),
+                                       _np_ptr(f), _np_ptr(g), _np_ptr(mi32))
+    L.check(rc, "pb200_objective_host")
+    return f, g, mi32

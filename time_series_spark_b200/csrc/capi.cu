@@ -262,10 +262,12 @@ PB200_API int pb200_synchronize(pb200_ctx* c) {
     return PB200_OK;
 }
 
-PB200_API int pb200_fit_device(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds, const void* d_y, int32_t y_dtype,
-                     const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
-                     const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
-                     int64_t* d_meta_i64, double* d_meta_f64) {
+}  // extern "C"
+
+static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds, const void* d_y, int32_t y_dtype,
+                    const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
+                    const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
+                    int64_t* d_meta_i64, double* d_meta_f64, const double* d_theta_in, double* d_grad_out) {
     if (!c) return fail(PB200_E_ARG, "ctx is null");
     int rc = check_opts(opts);
     if (rc) return rc;
@@ -403,6 +405,8 @@ PB200_API int pb200_fit_device(pb200_ctx* c, const pb200_options* opts, const in
             fa.pstride = L.pstride;
             fa.Tp = Tp;
             fa.ppad = ppad;
+            fa.theta_in = d_theta_in;
+            fa.grad_out = d_grad_out;
             fa.o = od;
             int occ = 0;
             CK(LAUNCH[mask](NT, opts->growth, fa, 0, smem, c->stream, &occ));
@@ -412,6 +416,57 @@ PB200_API int pb200_fit_device(pb200_ctx* c, const pb200_options* opts, const in
             c->launches++;
         }
     }
+    return PB200_OK;
+}
+
+extern "C" {
+
+PB200_API int pb200_fit_device(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds, const void* d_y, int32_t y_dtype,
+                     const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
+                     const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
+                     int64_t* d_meta_i64, double* d_meta_f64) {
+    return fit_impl(c, opts, d_ds, d_y, y_dtype, h_offsets, n_series, floor, cap_multiplier, d_cap, d_params, d_tchange,
+                    d_meta_i32, d_meta_i64, d_meta_f64, nullptr, nullptr);
+}
+
+PB200_API int pb200_objective_host(pb200_ctx* c, const pb200_options* opts, const int64_t* h_ds, const void* h_y,
+                                   int32_t y_dtype, const int64_t* h_offsets, int64_t n_series, double floor,
+                                   double cap_multiplier, const double* h_theta, double* h_f, double* h_grad,
+                                   int32_t* h_meta_i32) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (n_series <= 0) return n_series == 0 ? PB200_OK : fail(PB200_E_ARG, "n_series");
+    if (!h_ds || !h_y || !h_offsets || !h_theta || !h_f || !h_grad || !h_meta_i32) return fail(PB200_E_ARG, "null pointer");
+    if (y_dtype < 0 || y_dtype > 2) return fail(PB200_E_ARG, "y_dtype");
+    pb200_layout L;
+    pb200_get_layout(opts, &L);
+    CK(cudaSetDevice(c->device));
+    const int64_t R = h_offsets[n_series];
+    const size_t N = (size_t)n_series;
+    CK(c->d_ds.reserve((size_t)R * 8));
+    CK(c->d_y.reserve((size_t)R * y_elem(y_dtype)));
+    CK(c->d_params.reserve(N * L.pstride * 8));
+    CK(c->d_tchange.reserve(N * L.smax * 8));
+    CK(c->d_mi32.reserve(N * 8 * 4));
+    CK(c->d_mi64.reserve(N * 2 * 8));
+    CK(c->d_mf64.reserve(N * 4 * 8));
+    CK(c->d_yhat.reserve(N * L.pstride * 8));   // theta_in
+    CK(c->d_lo.reserve(N * L.pstride * 8));     // grad_out
+    CK(cudaMemcpyAsync(c->d_ds.p, h_ds, (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_y.p, h_y, (size_t)R * y_elem(y_dtype), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_yhat.p, h_theta, N * L.pstride * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_lo.p, 0, N * L.pstride * 8, c->stream));
+    rc = fit_impl(c, opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype, h_offsets, n_series, floor, cap_multiplier,
+                  nullptr, (double*)c->d_params.p, (double*)c->d_tchange.p, (int32_t*)c->d_mi32.p,
+                  (int64_t*)c->d_mi64.p, (double*)c->d_mf64.p, (const double*)c->d_yhat.p, (double*)c->d_lo.p);
+    if (rc) return rc;
+    std::vector<double> mf(N * 4);
+    CK(cudaMemcpyAsync(h_grad, c->d_lo.p, N * L.pstride * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_meta_i32, c->d_mi32.p, N * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(mf.data(), c->d_mf64.p, N * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < N; ++i) h_f[i] = mf[i * 4 + 3];
     return PB200_OK;
 }
 

@@ -1,0 +1,218 @@
+"""B200 drop-in for the reference's src/jobs/prophet_scorer.py.
+
+Same names and contracts -- ``forecast_time_series(config)``, ``extract_date``,
+``ProphetScorer(config).read_model_dataframe / convert_forecasts / write_forecasts``,
+``ProphetScorer.score`` -- same YAML keys (``io.models``, ``io.forecasts``,
+``forecast.periods``, ``forecast.frequency``), same models-table input and forecast CSV
+output ``(created_timestamp, series_id, dim_id, forecast_date, forecast_timestamp,
+forecast_quantity)``.  The per-model ``make_future_dataframe`` / ``predict`` / int-cast /
+floor-clamp body (reference :35-102) is one batched GPU call over all models.
+
+Optional keys beyond the reference: ``forecast.intervals`` (default false: the reference
+computes yhat_lower/yhat_upper inside Prophet.predict and drops them at :86; set true to get
+``yhat_lower``/``yhat_upper`` columns), ``forecast.uncertainty_samples`` (1000),
+``forecast.interval_width`` (0.8), ``forecast.seed``.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import shutil
+from datetime import datetime, timezone
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pyarrow.csv as pacsv
+import pyarrow.dataset as pads
+
+from .. import _lib as L
+from .. import batched, model_record
+from ..frame import Frame
+from .prophet_modeler import get_context
+
+FORECAST_SCHEMA = pa.schema([   # reference prophet_scorer.py:27-32
+    pa.field("series_id", pa.int32(), True),
+    pa.field("dim_id", pa.int32(), True),
+    pa.field("ds", pa.timestamp("ns"), True),
+    pa.field("yhat", pa.int32(), True),
+])
+
+
+# pandas 0.25 (the reference's pin) offset aliases that later pandas renamed
+_LEGACY_ALIASES = {"H": "h", "T": "min", "S": "s", "L": "ms", "U": "us", "N": "ns", "M": "ME", "BM": "BME",
+                   "Q": "QE", "BQ": "BQE", "A": "YE", "Y": "YE", "BA": "BYE", "BY": "BYE", "AS": "YS", "BAS": "BYS"}
+
+
+def _to_offset(frequency):
+    import re
+    import pandas as pd
+    try:
+        return pd.tseries.frequencies.to_offset(frequency)
+    except ValueError:
+        m = re.fullmatch(r"(-?\d*)([A-Za-z]+)(-.*)?", str(frequency))
+        if not m or m.group(2) not in _LEGACY_ALIASES:
+            raise
+        return pd.tseries.frequencies.to_offset(f"{m.group(1)}{_LEGACY_ALIASES[m.group(2)]}{m.group(3) or ''}")
+
+
+def frequency_to_future(last_ds_ns: np.ndarray, periods: int, frequency) -> np.ndarray:
+    """Prophet.make_future_dataframe(periods, freq, include_history=False) for every model
+    (reference :57-66): ``date_range(start=last, periods=periods+1, freq)``, keep ``> last``,
+    first ``periods``.  'W' is replaced by ``pd.offsets.Week()`` so weeks stay on the last
+    date's weekday (:59-62).  Fixed-width frequencies are pure int64 arithmetic; calendar
+    frequencies (e.g. 'M') go through pandas once per distinct last date."""
+    import pandas as pd
+    last = np.asarray(last_ds_ns, dtype=np.int64)
+    if isinstance(frequency, str) and frequency == "W":
+        frequency = pd.offsets.Week()
+    off = _to_offset(frequency)
+    nanos = None
+    if isinstance(off, pd.offsets.Week) and off.weekday is None:
+        nanos = 7 * 86400 * 10**9 * off.n
+    else:
+        try:
+            nanos = int(off.nanos)
+        except Exception:
+            nanos = None
+    if nanos is not None:
+        return batched.make_future(last, periods, nanos)
+    out = np.empty((last.size, periods), np.int64)
+    uniq, inv = np.unique(last, return_inverse=True)
+    for u_i, u in enumerate(uniq):
+        ld = pd.Timestamp(int(u))
+        dates = pd.date_range(start=ld, periods=periods + 1, freq=off)
+        dates = dates[dates > ld][:periods]
+        if len(dates) != periods:
+            raise ValueError("could not build the future frame for frequency %r" % (frequency,))
+        out[inv == u_i] = dates.values.astype("datetime64[ns]").astype(np.int64)[None, :]
+    return out
+
+
+class _ForecastTimeSeriesOp:
+    """Batched GROUPED_MAP operator over the models table."""
+
+    def __init__(self, config):
+        self.config = config
+
+    def apply_batched(self, table: pa.Table, keys) -> pa.Table:
+        if list(keys) != ["series_id", "dim_id"]:
+            raise ValueError("forecast_time_series groups by ('series_id', 'dim_id')")
+        fc = self.config["forecast"]
+        want_intervals = bool(fc.get("intervals", False))
+        if table.num_rows == 0:
+            return FORECAST_SCHEMA.empty_table()
+        # model is None -> "no model found", empty frame for that group (reference :51-55)
+        mcol = table["model"]
+        if mcol.null_count:
+            nulls = table.filter(pc.is_null(mcol))
+            for sid, did in zip(nulls["series_id"].to_pylist(), nulls["dim_id"].to_pylist()):
+                print(f"For series_id: {sid}, dim_id: {did}, no model found")
+            table = table.filter(pc.is_valid(mcol))
+            if table.num_rows == 0:
+                return FORECAST_SCHEMA.empty_table()
+        fitted, last_ds, info = model_record.decode(table["model"])
+        opts = batched.make_options(growth="logistic" if info["logistic"] else "linear",
+                                    seasonality_mode="multiplicative" if info["multiplicative"] else "additive",
+                                    n_changepoints=info["n_changepoints"],
+                                    interval_width=fc.get("interval_width", 0.8),
+                                    uncertainty_samples=fc.get("uncertainty_samples", 1000) if want_intervals else 0)
+        opts.yearly, opts.weekly, opts.daily = info["yearly"], info["weekly"], info["daily"]
+        # reference :46-47: floor / cap are read back from the FLOAT32 columns of the models table
+        floor = table["floor"].combine_chunks().to_numpy(zero_copy_only=False).astype(np.float64)
+        cap = table["cap"].combine_chunks().to_numpy(zero_copy_only=False).astype(np.float64)
+        periods = int(fc["periods"])
+        future = frequency_to_future(last_ds, periods, fc["frequency"])
+        ctx = get_context()
+        res = batched.predict_batch_host(ctx, opts, fitted, future, floor, cap, seed=int(fc.get("seed", 0)),
+                                         intervals=want_intervals)
+        sid = table["series_id"].combine_chunks().to_numpy(zero_copy_only=False).astype(np.int32)
+        did = table["dim_id"].combine_chunks().to_numpy(zero_copy_only=False).astype(np.int32)
+        ok = fitted.meta_i32[:, 4] >= 0
+        # "Negative forecast values found" log line (reference :76-79)
+        neg = np.flatnonzero(ok & (np.trunc(res.yhat).min(axis=1) < floor))
+        for i in neg[:100]:
+            print(f"Negative forecast values found for series_id: {int(sid[i])}, dim_id: {int(did[i])}")
+        cols = {
+            "series_id": pa.array(np.repeat(sid, periods), pa.int32()),
+            "dim_id": pa.array(np.repeat(did, periods), pa.int32()),
+            "ds": pa.array(future.reshape(-1), pa.int64()).cast(pa.timestamp("ns")),
+            "yhat": pa.array(res.yhat_int.reshape(-1), pa.int32()),
+        }
+        if want_intervals:
+            cols["yhat_lower"] = pa.array(res.yhat_lower.reshape(-1), pa.float64())
+            cols["yhat_upper"] = pa.array(res.yhat_upper.reshape(-1), pa.float64())
+        out = pa.table(cols)
+        if not ok.all():
+            out = out.filter(pa.array(np.repeat(ok, periods)))
+        return out
+
+    def __call__(self, pdf):
+        tbl = pa.Table.from_pandas(pdf, preserve_index=False)
+        return self.apply_batched(tbl, ["series_id", "dim_id"]).to_pandas()
+
+
+def forecast_time_series(config):
+    """Forecast using trained time series model (series_id, dim_id) -- reference :18-104."""
+    return _ForecastTimeSeriesOp(config)
+
+
+def extract_date(datetimestamp: datetime):
+    """reference :107-108."""
+    return datetimestamp.date().strftime("%Y-%m-%d")
+
+
+class ProphetScorer:
+    """Forecast quantities using trained models (reference :114-165)."""
+
+    def __init__(self, config, logger=None):
+        self.logger = logger or logging.getLogger(self.__class__.__name__)
+        self.config = config
+
+    def read_model_dataframe(self, spark=None) -> Frame:
+        dset = pads.dataset(self.config["io"]["models"], format="parquet")
+        return Frame(dset.to_table())
+
+    @staticmethod
+    def convert_forecasts(forecast_df: Frame) -> Frame:
+        """reference :131-145; the per-row Python date UDF becomes one vectorised strftime."""
+        created_timestamp = datetime.now(timezone.utc).replace(microsecond=0).isoformat()
+        t = forecast_df.table
+        n = t.num_rows
+        ds = t["ds"]
+        cols = {
+            "created_timestamp": pa.array([created_timestamp] * n, pa.string()) if n < 1024 else
+            pa.DictionaryArray.from_arrays(pa.array(np.zeros(n, np.int32)), pa.array([created_timestamp])).cast(pa.string()),
+            "series_id": t["series_id"],
+            "dim_id": t["dim_id"],
+            "forecast_date": pc.strftime(ds, format="%Y-%m-%d"),
+            "forecast_timestamp": ds,
+            "forecast_quantity": t["yhat"],
+        }
+        for extra in ("yhat_lower", "yhat_upper"):
+            if extra in t.column_names:
+                cols[extra] = t[extra]
+        return Frame(pa.table(cols))
+
+    def write_forecasts(self, output_df: Frame):
+        """CSV with header, mode='overwrite' (reference :147-150); a directory of part files."""
+        out = self.config["io"]["forecasts"]
+        rank = int(os.environ.get("RANK", "0"))
+        if rank == 0 and os.path.isdir(out):
+            shutil.rmtree(out)
+        os.makedirs(out, exist_ok=True)
+        t = output_df.table
+        if "forecast_timestamp" in t.column_names and pa.types.is_timestamp(t["forecast_timestamp"].type):
+            # Spark's CSV writer prints timestamps as yyyy-MM-dd'T'HH:mm:ss.SSSXXX by default
+            i = t.column_names.index("forecast_timestamp")
+            t = t.set_column(i, "forecast_timestamp", pc.strftime(t["forecast_timestamp"], format="%Y-%m-%dT%H:%M:%S.000Z"))
+        pacsv.write_csv(t, os.path.join(out, f"part-{rank:05d}.csv"),
+                        write_options=pacsv.WriteOptions(include_header=True, quoting_style="needed"))
+
+    @staticmethod
+    def score(spark_session, config):
+        scorer = ProphetScorer(config)
+        model_df = scorer.read_model_dataframe(spark_session)
+        forecast_df = model_df.groupby("series_id", "dim_id").apply(forecast_time_series(scorer.config))
+        converted_df = scorer.convert_forecasts(forecast_df)
+        scorer.write_forecasts(converted_df)
