@@ -95,6 +95,7 @@ struct pb200_ctx {
     DevBuf d_ds, d_y, d_cap, d_params, d_tchange, d_mi32, d_mi64, d_mf64;
     DevBuf d_fut, d_floor, d_yhat, d_lo, d_hi, d_yint;
     DevBuf d_mc;     // MC workspace
+    DevBuf d_planes; // fit kernel planes workspace (one slice per resident CTA)
     int lc_max[NLC];
 };
 
@@ -232,8 +233,8 @@ PB200_API pb200_ctx* pb200_create(int device) {
         delete c;
         return nullptr;
     }
-    c->lc_max[0] = env_int("PB200_LC0_MAX", 160);
-    c->lc_max[1] = env_int("PB200_LC1_MAX", 640);
+    c->lc_max[0] = env_int("PB200_LC0_MAX", 1 << 30);   // warp-per-series for every length
+    c->lc_max[1] = env_int("PB200_LC1_MAX", 1 << 30);
     c->lc_max[2] = 1 << 30;
     return c;
 }
@@ -244,7 +245,7 @@ PB200_API void pb200_destroy(pb200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_offsets, &c->d_order, &c->d_lenclass, &c->d_qitems, &c->d_qctl, &c->d_ds, &c->d_y, &c->d_cap,
                       &c->d_params, &c->d_tchange, &c->d_mi32, &c->d_mi64, &c->d_mf64, &c->d_fut, &c->d_floor, &c->d_yhat,
-                      &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc})
+                      &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc, &c->d_planes})
         b->release();
     c->h_ctl.release();
     cudaEventDestroy(c->ctl_ev);
@@ -317,16 +318,6 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             if (T > lc_tmax[lc]) lc_tmax[lc] = T;
         }
     }
-    // feasibility of the longest class in shared memory
-    const int nseas_max = (opts->yearly != 0) + (opts->weekly != 0) + (opts->daily != 0);
-    {
-        const int NT = LC_NT[NLC - 1];
-        const int chunk = (lc_tmax[NLC - 1] + NT - 1) / NT;
-        const size_t need = pb200::fit_smem_bytes(NT, nseas_max, chunk * NT, 64);
-        if (lc_n[NLC - 1] > 0 && need > 227 * 1024)
-            return fail(PB200_E_UNSUPPORTED, "series too long for the shared-memory-resident fit kernel");
-    }
-
     // ---- device control buffers ----
     CK(c->d_offsets.reserve((size_t)(N + 1) * 8));
     CK(c->d_order.reserve((size_t)N * 4));
@@ -372,20 +363,42 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         c->launches++;
     }
     // ---- fit kernels: one persistent launch per (length class, seasonality class) ----
+    // pass 1: launch geometry and the planes workspace (one slice per resident CTA)
+    struct Geo { int grid, Tp, ppad; size_t smem, slice, off; bool on; };
+    Geo geo[NLC][8];
+    size_t planes_bytes = 0;
+    for (int lc = 0; lc < NLC; ++lc)
+        for (int mask = 0; mask < 8; ++mask) {
+            Geo& g = geo[lc][mask];
+            g.on = false;
+            if (lc_n[lc] == 0) continue;
+            auto impossible = [&](int bit, int sw) { return (sw == 0 && (mask & bit)) || (sw == 1 && !(mask & bit)); };
+            if (impossible(1, opts->yearly) || impossible(2, opts->weekly) || impossible(4, opts->daily)) continue;
+            const int NT = LC_NT[lc];
+            const int chunk = std::max((lc_tmax[lc] + NT - 1) / NT, 1);
+            g.Tp = ((lc_tmax[lc] + chunk + 7) / 8) * 8;
+            const int K = mask_k(mask);
+            g.ppad = ((L.smax + (K > 0 ? K : 1) + 3) + 1) & ~1;
+            g.smem = pb200::fit_smem_bytes(NT, mask_nseas(mask), g.Tp, g.ppad);
+            int occ = 0;
+            FitArgs dummy{};
+            CK(LAUNCH[mask](NT, opts->growth, dummy, 0, g.smem, c->stream, &occ));
+            if (occ < 1) return fail(PB200_E_UNSUPPORTED, "fit kernel does not fit on an SM");
+            g.grid = (int)std::min<int64_t>((int64_t)lc_n[lc], (int64_t)c->sms * occ);
+            g.slice = (size_t)(1 + mask_nseas(mask)) * g.Tp;       // double2 elements
+            g.off = planes_bytes;
+            planes_bytes += (size_t)g.grid * g.slice * 16;
+            g.on = true;
+        }
+    CK(c->d_planes.reserve(planes_bytes));
     for (int lc = 0; lc < NLC; ++lc) {
         if (lc_n[lc] == 0) continue;
         const int NT = LC_NT[lc];
-        const int chunk = (lc_tmax[lc] + NT - 1) / NT;
-        const int Tp = std::max(chunk, 1) * NT;
         for (int mask = 0; mask < 8; ++mask) {
-            // seasonality classes that cannot occur under the options
-            auto impossible = [&](int bit, int sw) { return (sw == 0 && (mask & bit)) || (sw == 1 && !(mask & bit)); };
-            if (impossible(1, opts->yearly) || impossible(2, opts->weekly) || impossible(4, opts->daily)) continue;
-            const int K = mask_k(mask);
-            int ppad = L.smax + (K > 0 ? K : 1) + 3;
-            ppad = (ppad + 1) & ~1;
-            const size_t smem = pb200::fit_smem_bytes(NT, mask_nseas(mask), Tp, ppad);
-            if (smem > 227 * 1024) return fail(PB200_E_UNSUPPORTED, "series too long for shared memory");
+            const Geo& g = geo[lc][mask];
+            if (!g.on) continue;
+            const int Tp = g.Tp, ppad = g.ppad;
+            const size_t smem = g.smem;
             FitArgs fa;
             fa.ds = (const long long*)d_ds;
             fa.y = d_y;
@@ -405,14 +418,12 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             fa.pstride = L.pstride;
             fa.Tp = Tp;
             fa.ppad = ppad;
+            fa.planes = (double2*)((char*)c->d_planes.p + g.off);
+            fa.nseas_stride = (int)g.slice;
             fa.theta_in = d_theta_in;
             fa.grad_out = d_grad_out;
             fa.o = od;
-            int occ = 0;
-            CK(LAUNCH[mask](NT, opts->growth, fa, 0, smem, c->stream, &occ));
-            if (occ < 1) return fail(PB200_E_UNSUPPORTED, "fit kernel does not fit on an SM");
-            const int grid = (int)std::min<int64_t>((int64_t)lc_n[lc], (int64_t)c->sms * occ);
-            CK(LAUNCH[mask](NT, opts->growth, fa, grid, smem, c->stream, nullptr));
+            CK(LAUNCH[mask](NT, opts->growth, fa, g.grid, smem, c->stream, nullptr));
             c->launches++;
         }
     }

@@ -19,7 +19,6 @@ from __future__ import annotations
 import glob
 import logging
 import os
-import shutil
 import time
 
 import numpy as np
@@ -30,6 +29,7 @@ import pyarrow.parquet as pq
 
 from .. import _lib as L
 from .. import batched, model_record
+from .. import dist as pdist
 from ..frame import Frame
 from ..pack import pack_groups
 
@@ -90,6 +90,10 @@ class _ModelTimeSeriesOp:
         floor = self.config["model"]["floor"]
         cap_multiplier = self.config["model"]["cap_multiplier"]
         pk = pack_groups(table)
+        rank, ws, _ = pdist.world()
+        if ws > 1:      # one process per GPU: this rank fits its contiguous, row-balanced shard of the groups
+            lo, hi = pdist.shard_bounds(pk.offsets, ws)[rank]
+            pk = pk.take(lo, hi)
         if pk.n == 0:
             return MODEL_OUTPUT_SCHEMA.empty_table()
         opts = options_from_config(self.config)
@@ -164,15 +168,14 @@ class ProphetModeler:
     def persist_models(self, model_df: Frame):
         """Parquet, mode='overwrite' (reference :118-125); one part file per writer."""
         out = self.config["io"]["models"]
-        rank = int(os.environ.get("RANK", "0"))
-        if rank == 0 and os.path.isdir(out):
-            shutil.rmtree(out)
-        os.makedirs(out, exist_ok=True)
+        rank = pdist.world()[0]
+        pdist.prepare_output_dir(out)
         pq.write_table(model_df.table, os.path.join(out, f"part-{rank:05d}.parquet"))
 
     @staticmethod
     def model(spark_session, config):
         """Create the trained time series models (reference :127-143)."""
+        pdist.init_process_group()          # no-op unless launched by torchrun with WORLD_SIZE > 1
         scorer = ProphetModeler(config)
         input_df = scorer.read_input_dataframe(spark_session)
         model_df = input_df.groupby("series_id", "dim_id").apply(model_time_series(scorer.config))

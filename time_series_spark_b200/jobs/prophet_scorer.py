@@ -17,7 +17,6 @@ from __future__ import annotations
 
 import logging
 import os
-import shutil
 from datetime import datetime, timezone
 
 import numpy as np
@@ -28,6 +27,7 @@ import pyarrow.dataset as pads
 
 from .. import _lib as L
 from .. import batched, model_record
+from .. import dist as pdist
 from ..frame import Frame
 from .prophet_modeler import get_context
 
@@ -100,6 +100,10 @@ class _ForecastTimeSeriesOp:
             raise ValueError("forecast_time_series groups by ('series_id', 'dim_id')")
         fc = self.config["forecast"]
         want_intervals = bool(fc.get("intervals", False))
+        rank, ws, _ = pdist.world()
+        if ws > 1 and table.num_rows:      # shard the model rows across ranks (equal horizon => equal work)
+            lo, hi = pdist.shard_bounds(np.arange(table.num_rows + 1, dtype=np.int64), ws)[rank]
+            table = table.slice(lo, hi - lo)
         if table.num_rows == 0:
             return FORECAST_SCHEMA.empty_table()
         # model is None -> "no model found", empty frame for that group (reference :51-55)
@@ -197,10 +201,8 @@ class ProphetScorer:
     def write_forecasts(self, output_df: Frame):
         """CSV with header, mode='overwrite' (reference :147-150); a directory of part files."""
         out = self.config["io"]["forecasts"]
-        rank = int(os.environ.get("RANK", "0"))
-        if rank == 0 and os.path.isdir(out):
-            shutil.rmtree(out)
-        os.makedirs(out, exist_ok=True)
+        rank = pdist.world()[0]
+        pdist.prepare_output_dir(out)
         t = output_df.table
         if "forecast_timestamp" in t.column_names and pa.types.is_timestamp(t["forecast_timestamp"].type):
             # Spark's CSV writer prints timestamps as yyyy-MM-dd'T'HH:mm:ss.SSSXXX by default
@@ -211,6 +213,7 @@ class ProphetScorer:
 
     @staticmethod
     def score(spark_session, config):
+        pdist.init_process_group()          # no-op unless launched by torchrun with WORLD_SIZE > 1
         scorer = ProphetScorer(config)
         model_df = scorer.read_model_dataframe(spark_session)
         forecast_df = model_df.groupby("series_id", "dim_id").apply(forecast_time_series(scorer.config))

@@ -29,6 +29,12 @@ class PackedGroups:
     def n(self) -> int:
         return self.offsets.size - 1
 
+    def take(self, lo: int, hi: int) -> "PackedGroups":
+        """Groups [lo, hi) (a rank's shard; see dist.shard_bounds)."""
+        a, b = int(self.offsets[lo]), int(self.offsets[hi])
+        return PackedGroups(self.series_id[lo:hi], self.dim_id[lo:hi], self.offsets[lo:hi + 1] - a,
+                            self.ds[a:b], self.y[a:b], self.last_ds[lo:hi], self.n_rows_in[lo:hi])
+
 
 def _pinned_like(a: np.ndarray) -> np.ndarray:
     """Copy into page-locked memory when a CUDA runtime is usable (faster H2D), else return as is."""
