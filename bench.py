@@ -117,60 +117,40 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------
-def _cpu_fit_chunk(args):
-    lo, hi = args
-    sys.path.insert(0, ROOT)
-    from oracle import prophet_oracle as po
+def cpu_baseline(n_sample: int, cores: int, batch=None):
+    """Fits series [0, n_sample) of config #3 with the plain-C oracle (oracle/prophet_oracle.c: same
+    algorithm, per-segment sums, gcc -O2) on `cores` OpenMP threads.  Generation is outside the timing."""
+    from oracle import c_oracle as co
     from time_series_spark_b200 import synth
-    b = synth.config3(n=N_SERIES, lo=lo, hi=hi)
-    opts = po.ProphetOptions()
+    co.load()
+    b = batch if batch is not None else synth.config3(n=N_SERIES, lo=0, hi=n_sample)
+    y = b.y.astype(np.float64)
     t0 = time.perf_counter()
-    ev = 0
-    for i in range(b.n):
-        a, e = b.offsets[i], b.offsets[i + 1]
-        fr = po.fit(b.ds[a:e], b.y[a:e].astype(np.float64), 0.0, None, opts, cap_multiplier=1.1)
-        ev += fr.n_evals
-    return b.n, ev, time.perf_counter() - t0
-
-
-def cpu_baseline(n_sample: int, cores: int, pool=None):
-    """Fits series [0, n_sample) of config #3 with oracle/prophet_oracle.py, one process per core."""
-    import multiprocessing as mp
-    own = pool is None
-    if own:
-        pool = mp.get_context("spawn").Pool(cores)
-    per = max(1, n_sample // cores)
-    chunks = [(i * per, min(n_sample, (i + 1) * per)) for i in range((n_sample + per - 1) // per)]
-    t0 = time.perf_counter()
-    res = pool.map(_cpu_fit_chunk, chunks)
+    _, _, info = co.fit_batch(b.ds, y, b.offsets, 0.0, 1.1, nthreads=cores)
     wall = time.perf_counter() - t0
-    if own:
-        pool.close()
-    n = sum(r[0] for r in res)
+    n = b.n
     return {"value": n / wall, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n} series of the workload, oracle/prophet_oracle.py (numpy float64 restatement of "
-                      f"fbprophet 0.5 + Stan L-BFGS; NOT fbprophet itself), {cores} processes, {wall:.1f} s wall",
-            "mean_evals": sum(r[1] for r in res) / max(n, 1)}
+            "sample": f"first {n} series of the workload, oracle/prophet_oracle.c (plain-C float64 restatement of "
+                      f"fbprophet 0.5 + Stan L-BFGS with the same O(T*K) segment-sum objective as the GPU kernel; "
+                      f"NOT fbprophet itself), {cores} OpenMP threads, {wall:.2f} s wall",
+            "mean_evals": float(info[:, 2].mean())}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import multiprocessing as mp
+    from time_series_spark_b200 import synth
     cores = os.cpu_count() or 1
-    n_sample = max(cores, int(os.environ.get("PB200_CPU_SAMPLE", str(4 * cores))))
-    pool = mp.get_context("spawn").Pool(cores)
-    try:
-        for _ in range(args.warmup):
-            cpu_baseline(cores, cores, pool)
-        t0 = time.perf_counter()
-        last = None
-        for _ in range(args.steps):
-            last = cpu_baseline(n_sample, cores, pool)
-        wall = time.perf_counter() - t0
-    finally:
-        pool.close()
+    n_sample = int(os.environ.get("PB200_CPU_SAMPLE", str(max(256, 4 * cores))))
+    batch = synth.config3(n=N_SERIES, lo=0, hi=n_sample)
+    for _ in range(args.warmup):
+        cpu_baseline(min(n_sample, cores), cores, batch.take(0, min(n_sample, cores)))
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_baseline(n_sample, cores, batch)
+    wall = time.perf_counter() - t0
     value = args.steps * n_sample / wall
     last["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -178,7 +158,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample_series_per_step": n_sample,
                        "note": "fbprophet/pystan/pyspark are not installable here (no network, no JVM); the CPU arm is "
-                               "the oracle port of the same algorithm on all host cores"},
+                               "the C oracle port of the same algorithm on all host cores"},
             "cpu_baseline": last,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -279,7 +259,7 @@ def run_gpu(args):
     tps = _ncu_traffic_per_series()
     gflops = n_per * float(evals.mean()) * FLOPS_PER_EVAL / per_launch_s / 1e9
     cores = os.cpu_count() or 1
-    cpu = cpu_baseline(max(cores, int(os.environ.get("PB200_CPU_SAMPLE", str(8 * cores)))), cores) if world == 1 else None
+    cpu = cpu_baseline(int(os.environ.get("PB200_CPU_SAMPLE", str(max(256, 4 * cores)))), cores) if world == 1 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
