@@ -316,6 +316,10 @@ static int po_lbfgs(const po_prep* p, const po_opts* o, double* x, double* f_fin
                     for (;;) {
                         ++itNum;
                         if (fabs(alo - ahi) < 1e-16) { ret = 1; break; }
+                        { /* [guard, not in Stan] bracket = adjacent doubles: upstream would spin forever */
+                            const double mid = 0.5 * (alo + ahi);
+                            if (mid == alo || mid == ahi) { ret = 1; break; }
+                        }
                         if (itNum % 5 == 0) alpha = 0.5 * (alo + ahi);
                         else {
                             const double d1 = aloD + ahiD - 3 * (aloF - ahiF) / (alo - ahi);

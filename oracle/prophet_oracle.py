@@ -428,6 +428,12 @@ def _wolfe_zoom(func, x, f, dfp, c1dfp, c2dfp, p, alo, aloF, aloDFp, ahi, ahiF, 
         itNum += 1
         if abs(alo - ahi) < min_range:
             return 1, alpha, newX, newF, newDF
+        mid = 0.5 * (alo + ahi)
+        if mid == alo or mid == ahi:
+            # [guard, not in Stan] alo and ahi are adjacent doubles wider than min_range (|alpha| > ~0.5):
+            # upstream's loop cannot shrink the bracket any further and spins forever when the
+            # gradient has a kink (Laplace prior) inside it.  Observed on 1 of 200k config-#4 series.
+            return 1, alpha, newX, newF, newDF
         if itNum % 5 == 0:
             alpha = 0.5 * (alo + ahi)
         else:
