@@ -146,7 +146,7 @@ FitOptsDev to_dev(const pb200_options* o) {
     return d;
 }
 
-int mask_nseas(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
+int mask_nseas(int m) { return pb200::stored_planes((m & 1) ? 10 : 0, (m & 2) ? 3 : 0, (m & 4) ? 4 : 0); }   // stored planes
 int mask_k(int m) { return ((m & 1) ? 20 : 0) + ((m & 2) ? 6 : 0) + ((m & 4) ? 8 : 0); }
 
 size_t y_elem(int dt) { return dt == PB200_Y_F64 ? 8 : 4; }
