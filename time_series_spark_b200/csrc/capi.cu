@@ -379,7 +379,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             g.Tp = ((lc_tmax[lc] + chunk + 7) / 8) * 8;
             const int K = mask_k(mask);
             g.ppad = ((L.smax + (K > 0 ? K : 1) + 3) + 1) & ~1;
-            g.smem = pb200::fit_smem_bytes(NT, mask_nseas(mask), g.Tp, g.ppad);
+            g.smem = pb200::fit_smem_bytes(NT, 1 + mask_nseas(mask), g.ppad);
             int occ = 0;
             FitArgs dummy{};
             CK(LAUNCH[mask](NT, opts->growth, dummy, 0, g.smem, c->stream, &occ));
