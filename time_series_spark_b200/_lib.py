@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprophet_b200.so")
+_VARIANT = os.environ.get("PB200_VARIANT", "")          # dev only: load an A/B build (see build.py)
+LIB_PATH = os.path.join(_HERE, f"libprophet_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 
 ABI_VERSION = 1
 Y_I32, Y_F32, Y_F64 = 0, 1, 2

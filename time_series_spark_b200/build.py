@@ -15,14 +15,15 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_build")
-LIB = os.path.join(HERE, "libprophet_b200.so")
+_VARIANT = os.environ.get("PB200_VARIANT", "")          # dev only: A/B builds with PB200_NVCC_EXTRA flags
+OBJ = os.path.join(CSRC, "_build", _VARIANT) if _VARIANT else os.path.join(CSRC, "_build")
+LIB = os.path.join(HERE, f"libprophet_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + [f for f in os.environ.get("PB200_NVCC_EXTRA", "").split() if f]
 
 
 def _nvcc() -> str:

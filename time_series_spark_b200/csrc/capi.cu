@@ -97,6 +97,7 @@ struct pb200_ctx {
     DevBuf d_mc;     // MC workspace
     DevBuf d_planes; // fit kernel planes workspace (one slice per resident CTA)
     int lc_max[NLC];
+    bool lc_auto = true;   // false when PB200_LC*_MAX pins the CTA width
 };
 
 namespace {
@@ -236,6 +237,7 @@ PB200_API pb200_ctx* pb200_create(int device) {
     c->lc_max[0] = env_int("PB200_LC0_MAX", 1 << 30);   // warp-per-series for every length
     c->lc_max[1] = env_int("PB200_LC1_MAX", 1 << 30);
     c->lc_max[2] = 1 << 30;
+    c->lc_auto = !(getenv("PB200_LC0_MAX") || getenv("PB200_LC1_MAX"));
     return c;
 }
 
@@ -311,8 +313,11 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         for (int i = 0; i < N; ++i) {
             const int T = (int)(ho[i + 1] - ho[i]);
             horder[posv[(size_t)T]++] = i;
+            // CTA width: one warp per series fills the chip once there are >= ~8 series per SM; a small
+            // batch of long series gets 4 warps per series instead (same kernels, NT = 128)
             int lc = 0;
             while (lc < NLC - 1 && T > c->lc_max[lc]) ++lc;
+            if (c->lc_auto && N < c->sms * 8 && T >= 256) lc = NLC - 1;
             hlc[i] = lc;
             lc_n[lc]++;
             if (T > lc_tmax[lc]) lc_tmax[lc] = T;
