@@ -314,10 +314,11 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tps * n_per) if tps else None, "peak_source": peak_src,
-                     "kernel": "pb200::fit_kernel<128, true, 0, 3, 4>",
+                     "kernel": "pb200::fit_kernel<32, true, 0, 3, 4>",
                      "algorithmic_bytes_per_launch": n_per * ALG_BYTES_PER_SERIES,
-                     "note": "series stay in shared memory for ~700 objective evaluations: the kernel is FP64-issue "
-                             "bound, not HBM bound; see fp64 below",
+                     "note": "ds/y are read from HBM once per series; the ~700 objective evaluations stream the "
+                             "series' planes (32 B/point) from L2: the kernel is FP64-issue bound, not HBM bound; "
+                             "see fp64 below",
                      "fp64": {"achieved_gflops": gflops, "peak_gflops": FP64_PEAK_GFLOPS, "frac": gflops / FP64_PEAK_GFLOPS,
                               "flops_per_eval_model": FLOPS_PER_EVAL}},
     }
