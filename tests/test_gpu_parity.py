@@ -272,3 +272,34 @@ def test_edge_cases_status_codes(gpu_ctx):
     ds_bad[40], ds_bad[41] = ds_bad[41], ds_bad[40]
     fbad = batched.fit_batch_host(gpu_ctx, batched.make_options(), ds_bad, y, offsets, 0.0, 1.1)
     assert fbad.meta_i32[3, 4] == L.ST_BAD_INPUT
+
+
+def test_long_and_irregular_series(gpu_ctx):
+    """No shared-memory length limit (planes live in the L2-resident workspace): a 6000-point series
+    with gaps, duplicates and yearly+weekly+daily seasonality (K = 34, the largest class) fits and its
+    objective/gradient match the oracle."""
+    rng = np.random.RandomState(42)
+    step = 3 * 3600 * 10**9
+    idx = np.sort(rng.choice(np.arange(9000), 6000, replace=False))
+    idx[100:104] = idx[100]                      # duplicate timestamps
+    ds = (np.datetime64("2015-01-01T00:00:00", "ns").astype(np.int64) + step * idx).astype(np.int64)
+    days = (ds - ds[0]) / (86400 * 10**9)
+    y = (500 * (1 + 0.3 * np.sin(2 * np.pi * days / 365.25) + 0.1 * np.sin(2 * np.pi * days / 7) +
+                0.1 * np.sin(2 * np.pi * days)) * (1 + 0.2 * days / days.max()) + rng.normal(0, 15, ds.size))
+    y = np.maximum(np.rint(y), 1).astype(np.int32)
+    offsets = np.array([0, ds.size], np.int64)
+    opts, oopts = batched.make_options(), po.ProphetOptions()
+    p = po.prepare(ds, y.astype(np.float64), 0.0, float(y.max()) * 1.1, oopts)
+    assert (p.K, p.S) == (34, 25)
+    lay = L.get_layout(opts)
+    th = po.initial_theta(p) + 0.03 * rng.randn(p.S + p.K + 3)
+    row = np.zeros((1, lay.pstride))
+    row[0, :th.size] = th
+    f, g, mi = batched.objective_host(gpu_ctx, opts, ds, y, offsets, 0.0, 1.1, row)
+    err, fo, go = po.neg_logp_grad(th, p)
+    assert err == 0 and mi[0, 3] == 7
+    assert abs(f[0] - fo) <= 1e-10 * abs(fo)
+    assert np.max(np.abs(g[0, :th.size] - go)) <= 1e-8 * max(1.0, np.max(np.abs(go)))
+    fb = batched.fit_batch_host(gpu_ctx, opts, ds, y, offsets, 0.0, 1.1)
+    fr = po.fit(ds, y.astype(np.float64), opts=oopts)
+    assert fb.meta_i32[0, 4] >= 0 and abs(fb.meta_f64[0, 3] - fr.neg_logp) <= 5e-3 * abs(fr.neg_logp)

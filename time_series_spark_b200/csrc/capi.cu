@@ -105,7 +105,7 @@ namespace {
 using pb200::FitArgs;
 using pb200::FitOptsDev;
 
-typedef cudaError_t (*launch_fn)(int, int, const FitArgs&, int, size_t, cudaStream_t, int*);
+typedef cudaError_t (*launch_fn)(int, int, int, const FitArgs&, int, size_t, cudaStream_t, int*);
 const launch_fn LAUNCH[8] = {pb200::launch_fit_mask0, pb200::launch_fit_mask1, pb200::launch_fit_mask2,
                              pb200::launch_fit_mask3, pb200::launch_fit_mask4, pb200::launch_fit_mask5,
                              pb200::launch_fit_mask6, pb200::launch_fit_mask7};
@@ -327,18 +327,18 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     CK(c->d_offsets.reserve((size_t)(N + 1) * 8));
     CK(c->d_order.reserve((size_t)N * 4));
     CK(c->d_lenclass.reserve((size_t)N * 4));
-    CK(c->d_qitems.reserve((size_t)NLC * 8 * N * 4));
-    CK(c->d_qctl.reserve((size_t)NLC * 8 * 2 * 4));
+    CK(c->d_qitems.reserve((size_t)NLC * 16 * N * 4));
+    CK(c->d_qctl.reserve((size_t)NLC * 16 * 2 * 4));
     CK(cudaMemcpyAsync(c->d_offsets.p, ho, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_order.p, horder, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_lenclass.p, hlc, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ctl_ev, c->stream));
     c->ctl_pending = true;
-    CK(cudaMemsetAsync(c->d_qctl.p, 0, (size_t)NLC * 8 * 2 * 4, c->stream));
+    CK(cudaMemsetAsync(c->d_qctl.p, 0, (size_t)NLC * 16 * 2 * 4, c->stream));
     CK(cudaMemsetAsync(d_params, 0, (size_t)N * L.pstride * 8, c->stream));
     CK(cudaMemsetAsync(d_tchange, 0, (size_t)N * L.smax * 8, c->stream));
     int* q_count = (int*)c->d_qctl.p;
-    int* q_head = q_count + NLC * 8;
+    int* q_head = q_count + NLC * 16;
 
     const FitOptsDev od = to_dev(opts);
     // ---- prep kernel ----
@@ -370,13 +370,15 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     // ---- fit kernels: one persistent launch per (length class, seasonality class) ----
     // pass 1: launch geometry and the planes workspace (one slice per resident CTA)
     struct Geo { int grid, Tp, ppad; size_t smem, slice, off; bool on; };
-    Geo geo[NLC][8];
+    Geo geo[NLC][16];       // [length class][regular-grid variant * 8 + seasonality class]
     size_t planes_bytes = 0;
     for (int lc = 0; lc < NLC; ++lc)
-        for (int mask = 0; mask < 8; ++mask) {
-            Geo& g = geo[lc][mask];
+        for (int rm = 0; rm < 16; ++rm) {
+            const int mask = rm & 7, reg = rm >> 3;
+            Geo& g = geo[lc][rm];
             g.on = false;
             if (lc_n[lc] == 0) continue;
+            if (reg && mask == 0) continue;       // no Fourier features: nothing to regenerate
             auto impossible = [&](int bit, int sw) { return (sw == 0 && (mask & bit)) || (sw == 1 && !(mask & bit)); };
             if (impossible(1, opts->yearly) || impossible(2, opts->weekly) || impossible(4, opts->daily)) continue;
             const int NT = LC_NT[lc];
@@ -384,13 +386,15 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             g.Tp = ((lc_tmax[lc] + chunk + 7) / 8) * 8;
             const int K = mask_k(mask);
             g.ppad = ((L.smax + (K > 0 ? K : 1) + 3) + 1) & ~1;
-            g.smem = pb200::fit_smem_bytes(NT, 1 + mask_nseas(mask), g.ppad);
+            const int nst = reg ? 0 : mask_nseas(mask);                    // stored feature planes
+            const int nsa = (mask & 1) + ((mask >> 1) & 1) + ((mask >> 2) & 1);   // active seasonalities
+            g.smem = pb200::fit_smem_bytes(NT, 1 + nst, g.ppad, reg ? nsa : 0);
             int occ = 0;
             FitArgs dummy{};
-            CK(LAUNCH[mask](NT, opts->growth, dummy, 0, g.smem, c->stream, &occ));
+            CK(LAUNCH[mask](NT, opts->growth, reg, dummy, 0, g.smem, c->stream, &occ));
             if (occ < 1) return fail(PB200_E_UNSUPPORTED, "fit kernel does not fit on an SM");
             g.grid = (int)std::min<int64_t>((int64_t)lc_n[lc], (int64_t)c->sms * occ);
-            g.slice = (size_t)(1 + mask_nseas(mask)) * g.Tp;       // double2 elements
+            g.slice = (size_t)(1 + nst) * g.Tp;                   // double2 elements
             g.off = planes_bytes;
             planes_bytes += (size_t)g.grid * g.slice * 16;
             g.on = true;
@@ -399,8 +403,9 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     for (int lc = 0; lc < NLC; ++lc) {
         if (lc_n[lc] == 0) continue;
         const int NT = LC_NT[lc];
-        for (int mask = 0; mask < 8; ++mask) {
-            const Geo& g = geo[lc][mask];
+        for (int rm = 0; rm < 16; ++rm) {
+            const int mask = rm & 7, reg = rm >> 3;
+            const Geo& g = geo[lc][rm];
             if (!g.on) continue;
             const int Tp = g.Tp, ppad = g.ppad;
             const size_t smem = g.smem;
@@ -409,7 +414,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             fa.y = d_y;
             fa.y_dtype = y_dtype;
             fa.offsets = (const long long*)c->d_offsets.p;
-            const int q = lc * 8 + mask;
+            const int q = lc * 16 + rm;
             fa.q_items = (const int*)c->d_qitems.p + (size_t)q * N;
             fa.q_count = q_count + q;
             fa.q_head = q_head + q;
@@ -428,7 +433,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             fa.theta_in = d_theta_in;
             fa.grad_out = d_grad_out;
             fa.o = od;
-            CK(LAUNCH[mask](NT, opts->growth, fa, g.grid, smem, c->stream, nullptr));
+            CK(LAUNCH[mask](NT, opts->growth, reg, fa, g.grid, smem, c->stream, nullptr));
             c->launches++;
         }
     }

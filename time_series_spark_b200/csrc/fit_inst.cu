@@ -15,9 +15,9 @@ constexpr int YO = (PB200_MASK & 1) ? 10 : 0;
 constexpr int WO = (PB200_MASK & 2) ? 3 : 0;
 constexpr int DO = (PB200_MASK & 4) ? 4 : 0;
 
-template <int NT, bool LOGI>
+template <int NT, bool LOGI, bool REG>
 static cudaError_t launch_one(const FitArgs& a, int grid, size_t smem, cudaStream_t st, int* occ) {
-    auto kern = fit_kernel<NT, LOGI, YO, WO, DO>;
+    auto kern = fit_kernel<NT, LOGI, YO, WO, DO, REG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (occ) {
@@ -31,11 +31,19 @@ static cudaError_t launch_one(const FitArgs& a, int grid, size_t smem, cudaStrea
 #define PB200_CAT_(a, b) a##b
 #define PB200_CAT(a, b) PB200_CAT_(a, b)
 
-cudaError_t PB200_CAT(launch_fit_mask, PB200_MASK)(int nt, int logi, const FitArgs& a, int grid, size_t smem,
+template <int NT>
+static cudaError_t launch_nt(int logi, int reg, const FitArgs& a, int grid, size_t smem, cudaStream_t st, int* occ) {
+    if constexpr (PB200_MASK != 0) {        // the regular-grid variant only differs when there are Fourier features
+        if (reg) return logi ? launch_one<NT, true, true>(a, grid, smem, st, occ) : launch_one<NT, false, true>(a, grid, smem, st, occ);
+    }
+    return logi ? launch_one<NT, true, false>(a, grid, smem, st, occ) : launch_one<NT, false, false>(a, grid, smem, st, occ);
+}
+
+cudaError_t PB200_CAT(launch_fit_mask, PB200_MASK)(int nt, int logi, int reg, const FitArgs& a, int grid, size_t smem,
                                                    cudaStream_t st, int* occ) {
-    if (nt == 32) return logi ? launch_one<32, true>(a, grid, smem, st, occ) : launch_one<32, false>(a, grid, smem, st, occ);
-    if (nt == 64) return logi ? launch_one<64, true>(a, grid, smem, st, occ) : launch_one<64, false>(a, grid, smem, st, occ);
-    if (nt == 128) return logi ? launch_one<128, true>(a, grid, smem, st, occ) : launch_one<128, false>(a, grid, smem, st, occ);
+    if (nt == 32) return launch_nt<32>(logi, reg, a, grid, smem, st, occ);
+    if (nt == 64) return launch_nt<64>(logi, reg, a, grid, smem, st, occ);
+    if (nt == 128) return launch_nt<128>(logi, reg, a, grid, smem, st, occ);
     return cudaErrorInvalidValue;
 }
 

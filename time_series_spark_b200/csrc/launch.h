@@ -5,7 +5,7 @@
 namespace pb200 {
 struct FitArgs;
 #define PB200_DECL(m) \
-    cudaError_t launch_fit_mask##m(int nt, int logi, const FitArgs& a, int grid, size_t smem, cudaStream_t st, int* occ);
+    cudaError_t launch_fit_mask##m(int nt, int logi, int reg, const FitArgs& a, int grid, size_t smem, cudaStream_t st, int* occ);
 PB200_DECL(0) PB200_DECL(1) PB200_DECL(2) PB200_DECL(3) PB200_DECL(4) PB200_DECL(5) PB200_DECL(6) PB200_DECL(7)
 #undef PB200_DECL
 }  // namespace pb200

@@ -217,5 +217,18 @@ class ProphetScorer:
         scorer = ProphetScorer(config)
         model_df = scorer.read_model_dataframe(spark_session)
         forecast_df = model_df.groupby("series_id", "dim_id").apply(forecast_time_series(scorer.config))
+        if config["forecast"].get("gather", False) and pdist.world()[1] > 1:
+            # optional: one NCCL gather of the final forecast frame to rank 0 (the only collective on
+            # the path); default is one part file per rank, like Spark's output directory
+            t = forecast_df.table
+            cols = [np.ascontiguousarray(t[c].combine_chunks().to_numpy(zero_copy_only=False)) for c in t.column_names]
+            cols = [c.astype("datetime64[ns]").astype(np.int64) if c.dtype.kind == "M" else c for c in cols]
+            got = pdist.gather_rows(cols, dst=0)
+            if got is None:
+                pdist.prepare_output_dir(scorer.config["io"]["forecasts"])
+                return
+            arrays = [pa.array(a, pa.int64()).cast(pa.timestamp("ns")) if n == "ds" else pa.array(a)
+                      for n, a in zip(t.column_names, got)]
+            forecast_df = Frame(pa.table(dict(zip(t.column_names, arrays))).cast(t.schema))
         converted_df = scorer.convert_forecasts(forecast_df)
         scorer.write_forecasts(converted_df)
