@@ -142,7 +142,7 @@ def run_reference(args):
         return 0
     from time_series_spark_b200 import synth
     cores = os.cpu_count() or 1
-    n_sample = int(os.environ.get("PB200_CPU_SAMPLE", str(max(256, 4 * cores))))
+    n_sample = int(os.environ.get("PB200_CPU_SAMPLE", str(max(256, 16 * cores))))
     batch = synth.config3(n=N_SERIES, lo=0, hi=n_sample)
     for _ in range(args.warmup):
         cpu_baseline(min(n_sample, cores), cores, batch.take(0, min(n_sample, cores)))
@@ -299,7 +299,7 @@ def run_gpu(args):
     tps = _ncu_traffic_per_series()
     gflops = n_per * float(evals.mean()) * FLOPS_PER_EVAL / per_launch_s / 1e9
     cores = os.cpu_count() or 1
-    cpu = cpu_baseline(int(os.environ.get("PB200_CPU_SAMPLE", str(max(256, 4 * cores)))), cores) if world == 1 else None
+    cpu = cpu_baseline(int(os.environ.get("PB200_CPU_SAMPLE", str(max(256, 16 * cores)))), cores) if world == 1 else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,10 +314,10 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tps * n_per) if tps else None, "peak_source": peak_src,
-                     "kernel": "pb200::fit_kernel<32, true, 0, 3, 4>",
+                     "kernel": "pb200::fit_kernel<32, true, 0, 3, 4, true>",
                      "algorithmic_bytes_per_launch": n_per * ALG_BYTES_PER_SERIES,
                      "note": "ds/y are read from HBM once per series; the ~700 objective evaluations stream the "
-                             "series' planes (32 B/point) from L2: the kernel is FP64-issue bound, not HBM bound; "
+                             "series' planes (16 B/point on a regular grid) from L2: the kernel is FP64-issue bound, not HBM bound; "
                              "see fp64 below",
                      "fp64": {"achieved_gflops": gflops, "peak_gflops": FP64_PEAK_GFLOPS, "frac": gflops / FP64_PEAK_GFLOPS,
                               "flops_per_eval_model": FLOPS_PER_EVAL}},

@@ -138,6 +138,8 @@ FitOptsDev to_dev(const pb200_options* o) {
     d.changepoint_range = o->changepoint_range;
     d.tau = o->changepoint_prior_scale;
     d.seas_prior = o->seasonality_prior_scale;
+    d.rtau = 1.0 / o->changepoint_prior_scale;
+    d.inv_seas2 = 1.0 / (o->seasonality_prior_scale * o->seasonality_prior_scale);
     d.init_alpha = o->init_alpha;
     d.tol_obj = o->tol_obj;
     d.tol_rel_obj_eps = o->tol_rel_obj * eps;
