@@ -13,8 +13,8 @@
 // Philox4x32-10 keyed by (seed, model, draw), reproducible and shard-independent.
 //
 // One CTA per model; thread j owns draws j and j + 512; the draws of a tile of 16 future
-// points are staged in shared memory ([16][1024] fp64) and each warp sorts one row
-// (bitonic) to read the two order statistics.  Requires future timestamps ascending
+// points are staged in shared memory ([16][1024] fp64) and each warp sorts one row's order
+// statistics (256-bin histogram + exact selection inside the bin; bitonic sort as fallback).  Requires future timestamps ascending
 // within a model (make_future_dataframe's output is).
 #pragma once
 #include <cuda_runtime.h>
@@ -94,10 +94,105 @@ __device__ __forceinline__ void advance(DrawState& d, const ModelSm& ms, const d
     }
 }
 
+constexpr int MC_CAND = 64;    // candidates kept per histogram bin before falling back to a full sort
+
+// k-th smallest of the n values of `row` (k 0-based) by a 256-bin histogram + exact selection inside
+// the bin that holds rank k.  Returns false if that bin holds more than MC_CAND values.
+__device__ __forceinline__ bool kth_smallest(const double* row, const int n, const int k, const double mn,
+                                             const double scale, const int* hist, const int base, const int lsum,
+                                             double* cand, int* cnt, const int lane, double& out) {
+    // which lane's 8 bins contain rank k, and which bin
+    int b = -1, rb = 0;
+    if (k >= base && k < base + lsum) {
+        int cum = base;
+        for (int q = 0; q < 8; ++q) {
+            const int c = hist[lane * 8 + q];
+            if (k < cum + c) { b = lane * 8 + q; rb = k - cum; break; }
+            cum += c;
+        }
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, b >= 0);
+    const int src = __ffs(who) - 1;
+    b = __shfl_sync(0xffffffffu, b, src);
+    rb = __shfl_sync(0xffffffffu, rb, src);
+    if (lane == 0) *cnt = 0;
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+        const double v = row[e];
+        const int bb = min(255, (int)((v - mn) * scale));
+        if (bb == b) {
+            const int pos = atomicAdd(cnt, 1);
+            if (pos < MC_CAND) cand[pos] = v;
+        }
+    }
+    __syncwarp();
+    const int m = *cnt;
+    if (m > MC_CAND) return false;
+    // exact selection: the candidate with exactly rb candidates ordered before it
+    double found = 0.0;
+    int have = 0;
+    for (int i = lane; i < m; i += 32) {
+        const double vi = cand[i];
+        int r = 0;
+        for (int j = 0; j < m; ++j) {
+            const double vj = cand[j];
+            r += (vj < vi || (vj == vi && j < i)) ? 1 : 0;
+        }
+        if (r == rb) { found = vi; have = 1; }
+    }
+    const unsigned w2 = __ballot_sync(0xffffffffu, have);
+    out = __shfl_sync(0xffffffffu, found, __ffs(w2) - 1);
+    __syncwarp();
+    return w2 != 0;
+}
+
+// numpy percentile (linear interpolation) at the two interval bounds from the draws of one point
+__device__ __forceinline__ bool select_quantiles(const double* row, const int n, const int lo_i, const double lo_f,
+                                                 const int hi_i, const double hi_f, int* hist, double* cand, int* cnt,
+                                                 const int lane, double& lo_v, double& hi_v) {
+    double mn = INFINITY, mx = -INFINITY;
+    for (int e = lane; e < n; e += 32) { const double v = row[e]; mn = fmin(mn, v); mx = fmax(mx, v); }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (!(mx > mn) || !isfinite(mx - mn)) {
+        if (mx == mn) { lo_v = hi_v = mn; return true; }
+        return false;
+    }
+    const double scale = 256.0 / (mx - mn);
+    for (int q = 0; q < 8; ++q) hist[lane * 8 + q] = 0;
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) atomicAdd(&hist[min(255, (int)((row[e] - mn) * scale))], 1);
+    __syncwarp();
+    int lsum = 0;
+    for (int q = 0; q < 8; ++q) lsum += hist[lane * 8 + q];
+    int inc = lsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const int base = inc - lsum;
+    double v[4];
+    const int ranks[4] = {lo_i, min(lo_i + 1, n - 1), hi_i, min(hi_i + 1, n - 1)};
+    for (int q = 0; q < 4; ++q) {
+        if (q > 0 && ranks[q] == ranks[q - 1]) { v[q] = v[q - 1]; continue; }
+        if (!kth_smallest(row, n, ranks[q], mn, scale, hist, base, lsum, cand, cnt, lane, v[q])) return false;
+    }
+    lo_v = v[0] + (v[1] - v[0]) * lo_f;
+    hi_v = v[2] + (v[3] - v[2]) * hi_f;
+    return true;
+}
+
 template <bool LOGI>
 __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const McArgs a) {
     extern __shared__ __align__(16) unsigned char mc_smem[];
     double* rows = (double*)mc_smem;                       // [MC_TILE][MC_NP]
+    double* cand = rows + MC_TILE * MC_NP;                 // [MC_THREADS/32][MC_CAND]
+    int* hist = (int*)(cand + (MC_THREADS / 32) * MC_CAND);   // [MC_THREADS/32][256]
+    int* cnt = hist + (MC_THREADS / 32) * 256;             // [MC_THREADS/32]
     __shared__ ModelSm ms;
     __shared__ double seas[MC_TILE], tt[MC_TILE];
     __shared__ double red_t[MC_THREADS / 32];
@@ -177,28 +272,34 @@ __global__ void __launch_bounds__(MC_THREADS, 1) mc_kernel(const McArgs a) {
                 }
             }
             __syncthreads();
-            // ---- percentiles: warp w sorts row w (bitonic over MC_NP doubles) ----
+            // ---- percentiles: warp w selects the order statistics of row w ----
             if (warp < np) {
                 double* row = rows + warp * MC_NP;
-                for (int k = 2; k <= MC_NP; k <<= 1) {
-                    for (int j = k >> 1; j > 0; j >>= 1) {
-                        for (int e = lane; e < MC_NP / 2; e += 32) {
-                            // e-th compare-exchange of this stage: indices i < l differing in bit j
-                            const int i = ((e & ~(j - 1)) << 1) | (e & (j - 1));
-                            const int l = i | j;
-                            const bool up = (i & k) == 0;
-                            const double x = row[i], y = row[l];
-                            const bool sw = up ? (x > y) : (x < y);
-                            if (sw) { row[i] = y; row[l] = x; }
+                double lo_v, hi_v;
+                if (!select_quantiles(row, a.n_samples, a.lo_i, a.lo_f, a.hi_i, a.hi_f, hist + warp * 256,
+                                      cand + warp * MC_CAND, cnt + warp, lane, lo_v, hi_v)) {
+                    // fallback (a histogram bin too crowded): full bitonic sort of the row
+                    for (int k = 2; k <= MC_NP; k <<= 1) {
+                        for (int j = k >> 1; j > 0; j >>= 1) {
+                            for (int e = lane; e < MC_NP / 2; e += 32) {
+                                const int i = ((e & ~(j - 1)) << 1) | (e & (j - 1));
+                                const int l = i | j;
+                                const bool up = (i & k) == 0;
+                                const double x = row[i], y = row[l];
+                                const bool sw = up ? (x > y) : (x < y);
+                                if (sw) { row[i] = y; row[l] = x; }
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
-                }
-                if (lane == 0) {
                     const double l0 = row[a.lo_i], l1 = row[min(a.lo_i + 1, a.n_samples - 1)];
                     const double u0 = row[a.hi_i], u1 = row[min(a.hi_i + 1, a.n_samples - 1)];
-                    a.lower[base + h0 + warp] = l0 + (l1 - l0) * a.lo_f;
-                    a.upper[base + h0 + warp] = u0 + (u1 - u0) * a.hi_f;
+                    lo_v = l0 + (l1 - l0) * a.lo_f;
+                    hi_v = u0 + (u1 - u0) * a.hi_f;
+                }
+                if (lane == 0) {
+                    a.lower[base + h0 + warp] = lo_v;
+                    a.upper[base + h0 + warp] = hi_v;
                 }
             }
             __syncthreads();
@@ -220,7 +321,7 @@ inline int launch_mc(cudaStream_t st, int sms, const PredictArgs& p, int n_sampl
     a.seed = seed;
     a.lower = lower;
     a.upper = upper;
-    const size_t smem = (size_t)MC_TILE * MC_NP * 8;
+    const size_t smem = (size_t)MC_TILE * MC_NP * 8 + (size_t)(MC_THREADS / 32) * (MC_CAND * 8 + 256 * 4 + 4) + 16;
     const int grid = p.n_models < sms ? p.n_models : sms;
     cudaError_t e;
     if (p.growth == PB200_GROWTH_LOGISTIC) {
