@@ -31,7 +31,7 @@ from .. import _lib as L
 from .. import batched, model_record
 from .. import dist as pdist
 from ..frame import Frame
-from ..pack import pack_groups
+from ..pack import pack_groups, pack_groups_cuda
 
 # reference prophet_modeler.py:12-17 (Spark StructType -> Arrow)
 MODEL_INPUT_SCHEMA = pa.schema([
@@ -89,7 +89,11 @@ class _ModelTimeSeriesOp:
             raise ValueError("model_time_series groups by ('series_id', 'dim_id')")
         floor = self.config["model"]["floor"]
         cap_multiplier = self.config["model"]["cap_multiplier"]
-        pk = pack_groups(table)
+        ctx = get_context()
+        # group + sort on the GPU (two radix sorts), ds / y stay in HBM for the fit
+        import torch
+        torch.cuda.set_device(ctx.device)
+        pk = pack_groups_cuda(table, device=f"cuda:{ctx.device}")
         rank, ws, _ = pdist.world()
         if ws > 1:      # one process per GPU: this rank fits its contiguous, row-balanced shard of the groups
             lo, hi = pdist.shard_bounds(pk.offsets, ws)[rank]
@@ -102,8 +106,8 @@ class _ModelTimeSeriesOp:
         # keep that observable behaviour (prophet_modeler.py:81 only catches RuntimeError)
         if np.any(np.diff(pk.offsets) < 2):
             raise ValueError("Dataframe has less than 2 non-NaN rows.")
-        ctx = get_context()
-        fitted = batched.fit_batch_host(ctx, opts, pk.ds, pk.y, pk.offsets, float(floor), float(cap_multiplier))
+        fitted = batched.fit_batch_device(ctx, opts, pk.ds.contiguous(), pk.y.contiguous(), pk.offsets,
+                                          float(floor), float(cap_multiplier)).to_host()
         status = fitted.meta_i32[:, 4]
         if np.any(status == L.ST_CAP_LE_FLOOR):
             raise ValueError("cap must be greater than floor (which defaults to 0).")

@@ -35,6 +35,10 @@ class PackedGroups:
         return PackedGroups(self.series_id[lo:hi], self.dim_id[lo:hi], self.offsets[lo:hi + 1] - a,
                             self.ds[a:b], self.y[a:b], self.last_ds[lo:hi], self.n_rows_in[lo:hi])
 
+    @property
+    def on_device(self) -> bool:
+        return not isinstance(self.ds, np.ndarray)
+
 
 def _pinned_like(a: np.ndarray) -> np.ndarray:
     """Copy into page-locked memory when a CUDA runtime is usable (faster H2D), else return as is."""
@@ -113,3 +117,56 @@ def pack_groups(table: pa.Table, keys=("series_id", "dim_id"), ds_col="ds", y_co
     if pin:
         ds_np, y_np = _pinned_like(ds_np), _pinned_like(y_np)
     return PackedGroups(sid, did, offsets, ds_np, y_np, last_ds.astype(np.int64), n_rows_in)
+
+
+def pack_groups_cuda(table: pa.Table, device=None, keys=("series_id", "dim_id"), ds_col="ds", y_col="y"):
+    """GPU version of :func:`pack_groups`: the (series_id, dim_id, ds) sort of the whole
+    frame runs on the B200 as two stable radix sorts (``torch.sort`` -- plumbing, not a hand-written
+    kernel) and ``ds`` / ``y`` stay resident in HBM for ``pb200_fit_device``.  Returns a PackedGroups
+    whose ``ds`` / ``y`` are CUDA tensors; ids, offsets and last_ds are host numpy arrays.
+    Null ``y`` rows are dropped exactly as on the host path."""
+    import torch
+    if table.num_rows == 0:
+        return pack_groups(table, keys, ds_col, y_col, pin=False)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ds_arr = table[ds_col]
+    if pa.types.is_timestamp(ds_arr.type):
+        if ds_arr.null_count:
+            raise ValueError("Found NaN in column ds.")
+        ds_arr = pc.cast(pc.cast(ds_arr, pa.timestamp("ns")), pa.int64())
+    ds_np = np.asarray(ds_arr.combine_chunks().to_numpy(zero_copy_only=False), dtype=np.int64)
+    k0 = np.asarray(table[keys[0]].combine_chunks().to_numpy(zero_copy_only=False)).astype(np.int64)
+    k1 = np.asarray(table[keys[1]].combine_chunks().to_numpy(zero_copy_only=False)).astype(np.int64)
+    ycol = table[y_col].combine_chunks()
+    integral = pa.types.is_integer(ycol.type)
+    if integral:
+        y_null = np.asarray(ycol.is_null().to_numpy(zero_copy_only=False)) if ycol.null_count else None
+        y_np = np.asarray(ycol.fill_null(0).to_numpy(zero_copy_only=False)).astype(np.int32)
+    else:
+        y_np = np.asarray(ycol.to_numpy(zero_copy_only=False)).astype(np.float64)
+        y_null = np.isnan(y_np) if np.isnan(y_np).any() else None
+    key = torch.from_numpy((k0 << 32) | (k1 & 0xFFFFFFFF)).to(dev)
+    ds_t = torch.from_numpy(ds_np).to(dev)
+    y_t = torch.from_numpy(y_np).to(dev)
+    i1 = torch.argsort(ds_t, stable=True)
+    i2 = torch.argsort(key[i1], stable=True)
+    order = i1[i2]
+    key, ds_t, y_t = key[order], ds_t[order], y_t[order]
+    new_grp = torch.ones(key.numel(), dtype=torch.bool, device=dev)
+    new_grp[1:] = key[1:] != key[:-1]
+    starts = torch.nonzero(new_grp).flatten()
+    ends = torch.cat((starts[1:], torch.tensor([key.numel()], device=dev)))
+    last_ds = ds_t[ends - 1].cpu().numpy()
+    n_rows_in = (ends - starts).cpu().numpy().astype(np.int64)
+    gkeys = key[starts].cpu().numpy()
+    sid, did = (gkeys >> 32).astype(np.int32), (gkeys & 0xFFFFFFFF).astype(np.int64).astype(np.int32)
+    if y_null is not None and y_null.any():
+        keep = ~torch.from_numpy(y_null).to(dev)[order]
+        grp_id = torch.cumsum(new_grp.to(torch.int64), 0) - 1
+        counts = torch.bincount(grp_id[keep], minlength=starts.numel()).cpu().numpy().astype(np.int64)
+        ds_t, y_t = ds_t[keep].contiguous(), y_t[keep].contiguous()
+    else:
+        counts = n_rows_in
+    offsets = np.zeros(sid.size + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    return PackedGroups(sid, did, offsets, ds_t.contiguous(), y_t.contiguous(), last_ds.astype(np.int64), n_rows_in)
