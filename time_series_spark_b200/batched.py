@@ -196,19 +196,24 @@ def predict_batch_host(ctx: L.Context, opts: L.Options, fitted: FittedBatch, fut
 
 
 def predict_batch_device(ctx: L.Context, opts: L.Options, fitted: FittedBatch, future_ds, floor, cap,
-                         seed: int = 0, intervals: bool = True, sync: bool = True) -> ForecastBatch:
-    """pb200_predict_device with torch CUDA tensors."""
+                         seed: int = 0, intervals: bool = True, sync: bool = True,
+                         out: Optional["ForecastBatch"] = None) -> ForecastBatch:
+    """pb200_predict_device with torch CUDA tensors (``out`` reuses a previous result's buffers)."""
     import torch
     n = fitted.n
     h = int(future_ds.shape[1])
     dev = future_ds.device
-    yhat = torch.empty((n, h), dtype=torch.float64, device=dev)
-    yint = torch.empty((n, h), dtype=torch.int32, device=dev)
     do_mc = intervals and opts.uncertainty_samples > 0
-    lo = torch.empty((n, h), dtype=torch.float64, device=dev) if do_mc else None
-    hi = torch.empty((n, h), dtype=torch.float64, device=dev) if do_mc else None
+    if out is not None:
+        yhat, yint, lo, hi = out.yhat, out.yhat_int, out.yhat_lower, out.yhat_upper
+    else:
+        yhat = torch.empty((n, h), dtype=torch.float64, device=dev)
+        yint = torch.empty((n, h), dtype=torch.int32, device=dev)
+        lo = torch.empty((n, h), dtype=torch.float64, device=dev) if do_mc else None
+        hi = torch.empty((n, h), dtype=torch.float64, device=dev) if do_mc else None
     if n > 0 and h > 0:
-        torch.cuda.current_stream(dev).synchronize()
+        if out is None:
+            torch.cuda.current_stream(dev).synchronize()
         rc = L.load().pb200_predict_device(
             ctx.handle, C.byref(opts), fitted.params.data_ptr(), fitted.tchange.data_ptr(),
             fitted.meta_i32.data_ptr(), fitted.meta_i64.data_ptr(), fitted.meta_f64.data_ptr(), n,
