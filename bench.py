@@ -226,6 +226,8 @@ def run_gpu(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
     host = out.to_host()
+    vc = ctx.last_fit_variant_counts()          # which fit-kernel variant the series of the last step ran on
+    variants = {name: int(vc[i].sum()) for i, name in enumerate(("planes", "rotation", "week_table", "day_table")) if vc[i].sum()}
     st = host.meta_i32[:, 4]
     evals = host.meta_i32[:, 6].astype(np.float64)
     fitted_ok = int((st >= 0).sum())
@@ -313,18 +315,20 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "series_per_gpu": n_per, "points_per_series": T_POINTS,
                    "global_series": world * n_per, "parallelism": f"series-sharded x{world}, no data-path collective",
                    "l2": f"inputs {(b.ds.nbytes + b.y.nbytes) / 1e6:.0f} MB per GPU, larger than the 126 MB L2",
-                   "mean_objective_evals_per_series": float(evals.mean()), "series_with_model": fitted_ok},
+                   "mean_objective_evals_per_series": float(evals.mean()), "series_with_model": fitted_ok,
+                   "fit_kernel_variants": variants},
         "e2e": {"value": world * n_per * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "pb200_fit_host (C ABI, pinned host buffers)", "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tps * n_per) if tps else None, "peak_source": peak_src,
-                     "kernel": "pb200::fit_kernel<32, true, 0, 3, 4, true>",
+                     "kernel": "pb200::fit_kernel<32, true, 0, 3, 4, 3>  (warp per series, logistic, weekly 3 + daily 4, day-table variant)",
                      "algorithmic_bytes_per_launch": n_per * ALG_BYTES_PER_SERIES,
                      "note": "ds/y are read from HBM once per series; the ~700 objective evaluations stream the "
-                             "series' planes (16 B/point on a regular grid) from L2: the kernel is FP64-issue bound, not HBM bound; "
-                             "see fp64 below",
+                             "series' planes (16 B/point on a regular grid) from L2: the kernel is FP64-issue / instruction-fetch bound, "
+                             "not HBM bound; see fp64 below (model flops of the plain T x K formulation -- the day-table "
+                             "variant executes fewer)",
                      "fp64": {"achieved_gflops": gflops, "peak_gflops": FP64_PEAK_GFLOPS, "frac": gflops / FP64_PEAK_GFLOPS,
                               "flops_per_eval_model": FLOPS_PER_EVAL}},
     }

@@ -129,6 +129,12 @@ PB200_API const char* pb200_last_error(void);
 PB200_API void* pb200_stream(pb200_ctx* ctx);
 /* number of kernel launches issued by this context so far */
 PB200_API int64_t pb200_launch_count(pb200_ctx* ctx);
+/* Diagnostics: how many series of the context's LAST fit went to each fit-kernel variant.
+ * counts[v*8 + mask], summed over the CTA-width classes; v = 0 feature planes, 1 regular-grid rotation,
+ * 2 week-period seasonal table, 3 day-period seasonal table; mask = bit0 yearly | bit1 weekly |
+ * bit2 daily.  Synchronises the context's stream. */
+#define PB200_N_VARIANT_COUNTS 32
+PB200_API int pb200_last_fit_variant_counts(pb200_ctx* ctx, int32_t* h_counts);
 
 /*
  * Batched fit: all series of a shard in one call.

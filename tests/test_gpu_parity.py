@@ -17,6 +17,8 @@ Stated tolerances (FP, relative to y_scale unless noted):
   objective at the returned optimum     |f_gpu - f_oracle| / |f|: median <= 5e-4, max <= 5e-3
   MC interval bounds                    within 0.05 sigma_obs*y_scale of the oracle's own 1000-draw bounds (mean)
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -117,6 +119,10 @@ def test_fit_reference_fixture(gpu_ctx, golden_input, golden_oracle):
 
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
 def test_fit_and_forecast_match_oracle_within_stated_tolerance(gpu_ctx, case):
+    _check_fit_and_forecast(gpu_ctx, case)
+
+
+def _check_fit_and_forecast(gpu_ctx, case):
     name, b, opts, oopts, freq = case
     fb = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
     last = b.ds[b.offsets[1:] - 1]
@@ -303,3 +309,106 @@ def test_long_and_irregular_series(gpu_ctx):
     fb = batched.fit_batch_host(gpu_ctx, opts, ds, y, offsets, 0.0, 1.1)
     fr = po.fit(ds, y.astype(np.float64), opts=oopts)
     assert fb.meta_i32[0, 4] >= 0 and abs(fb.meta_f64[0, 3] - fr.neg_logp) <= 5e-3 * abs(fr.neg_logp)
+
+
+# ---------------------------------------------------------------------------------------
+# seasonal-table kernel variants (fit_kernel.cuh point_pass_tab): the production path of a full-size
+# batch of regular 10..60-minute series.  Small batches of long series default to 4 warps per series,
+# so these tests pin one warp per series (PB200_LC0_MAX, read at pb200_create) to reach the variants,
+# and check with pb200_last_fit_variant_counts that they really ran.
+# ---------------------------------------------------------------------------------------
+def _ctx_with_env(**env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return L.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.fixture(scope="module")
+def warp_ctx():
+    c = _ctx_with_env(PB200_LC0_MAX=1 << 30)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def warp_ctx_no_tab():
+    c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_NO_TAB=1)
+    yield c
+    c.close()
+
+
+def _regrid(b, step_ns, T=None):
+    """The series of a synthetic batch on another regular grid (same values, other cadence / length)."""
+    T0 = int(b.offsets[1] - b.offsets[0])
+    T = T0 if T is None else T
+    y = b.y.reshape(b.n, T0)[:, :T]
+    grid = b.ds[0] + step_ns * np.arange(T, dtype=np.int64)
+    return synth.RaggedBatch(b.series_id, b.dim_id, np.arange(b.n + 1, dtype=np.int64) * T, np.tile(grid, b.n),
+                             np.ascontiguousarray(y).reshape(-1))
+
+
+def _tab_cases():
+    c3 = synth.config3(n=16)
+    H = 3600 * 10**9
+    return [
+        ("day_table_15min", c3, 3),                          # config #3 itself: P = 96
+        ("day_table_15min_T1400", _regrid(c3, NS15, 1400), 3),   # chunk 44 would collide (44 * 24 = 11 P): widened to 45
+        ("day_table_20min", _regrid(c3, 20 * 60 * 10**9), 3),    # P = 72, 20 days (chunk 45 -> 46)
+        ("week_table_hourly", _regrid(c3, H), 2),            # P = 168, 60 days
+        ("week_table_hourly_T337", _regrid(c3, H, 337), 2),  # two weeks + 1 point: the shortest series with weekly
+        ("week_table_2h", _regrid(c3, 2 * H), 2),            # P = 84, 120 days
+        ("rotation_30min", _regrid(c3, 30 * 60 * 10**9), 1),     # P = 48 < 64 bins: no conflict-free pairing
+        ("rotation_25min", _regrid(c3, 25 * 60 * 10**9), 1),   # step divides neither day nor week: no table
+    ]
+
+
+@pytest.mark.parametrize("case", _tab_cases(), ids=lambda c: c[0])
+def test_table_variants_objective_and_gradient(warp_ctx, warp_ctx_no_tab, case):
+    name, b, variant = case
+    opts, oopts = batched.make_options(), po.ProphetOptions()
+    lay = L.get_layout(opts)
+    rng = np.random.RandomState(5)
+    thetas, preps = [], []
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        y = b.y[a:e].astype(np.float64)
+        p = po.prepare(b.ds[a:e], y, 0.0, y.max() * 1.1, oopts)
+        th = po.initial_theta(p) + 0.05 * rng.randn(p.S + p.K + 3)
+        row = np.zeros(lay.pstride)
+        row[:th.size] = th
+        thetas.append(row)
+        preps.append((p, th))
+    th = np.array(thetas)
+    f, g, mi = batched.objective_host(warp_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1, th)
+    counts = warp_ctx.last_fit_variant_counts()
+    assert counts[variant, 6] == b.n and counts.sum() == b.n, (name, counts)
+    f0, g0, _ = batched.objective_host(warp_ctx_no_tab, opts, b.ds, b.y, b.offsets, 0.0, 1.1, th)
+    c0 = warp_ctx_no_tab.last_fit_variant_counts()
+    assert c0[1, 6] == b.n, (name, c0)
+    for i, (p, t) in enumerate(preps):
+        err, fo, go = po.neg_logp_grad(t, p)
+        assert err == 0 and mi[i, 4] == 0 and mi[i, 3] == 6
+        assert abs(f[i] - fo) <= 1e-10 * max(1.0, abs(fo)), (name, i, f[i], fo)
+        gd = np.max(np.abs(g[i, :t.size] - go)) / max(1.0, np.max(np.abs(go)))
+        assert gd <= 1e-8, (name, i, gd)
+        # table and rotation variants are the same sums in another order
+        assert abs(f[i] - f0[i]) <= 1e-11 * max(1.0, abs(fo))
+        assert np.max(np.abs(g[i] - g0[i])) <= 1e-9 * max(1.0, np.max(np.abs(go)))
+
+
+@pytest.mark.parametrize("which", ["day_table_15min", "week_table_hourly"])
+def test_table_variants_fit_and_forecast(warp_ctx, which):
+    b, variant = {c[0]: (c[1], c[2]) for c in _tab_cases()}[which]
+    freq = NS15 if variant == 3 else 3600 * 10**9
+    _check_fit_and_forecast(warp_ctx, (which, b, batched.make_options(), po.ProphetOptions(), freq))
+    assert warp_ctx.last_fit_variant_counts()[variant, 6] == b.n
+    fb = batched.fit_batch_host(warp_ctx, batched.make_options(), b.ds, b.y, b.offsets, 0.0, 1.1)
+    fb2 = batched.fit_batch_host(warp_ctx, batched.make_options(), b.ds, b.y, b.offsets, 0.0, 1.1)
+    assert np.array_equal(fb.params, fb2.params) and np.array_equal(fb.meta_i32, fb2.meta_i32)   # deterministic

@@ -44,7 +44,7 @@ class Layout(C.Structure):
 
 EXPORTS = [
     "pb200_default_options", "pb200_get_layout", "pb200_create", "pb200_destroy", "pb200_last_error",
-    "pb200_stream", "pb200_launch_count", "pb200_fit_device", "pb200_fit_host", "pb200_predict_device",
+    "pb200_stream", "pb200_launch_count", "pb200_last_fit_variant_counts", "pb200_fit_device", "pb200_fit_host", "pb200_predict_device",
     "pb200_predict_host", "pb200_make_future_device", "pb200_synchronize", "pb200_objective_host",
 ]
 
@@ -77,6 +77,8 @@ def load() -> C.CDLL:
     lib.pb200_stream.restype = vp
     lib.pb200_launch_count.argtypes = [vp]
     lib.pb200_launch_count.restype = i64
+    lib.pb200_last_fit_variant_counts.argtypes = [vp, vp]
+    lib.pb200_last_fit_variant_counts.restype = C.c_int
     fit_args = [vp, OP, vp, vp, i32, vp, i64, dbl, dbl, vp, vp, vp, vp, vp, vp]
     lib.pb200_fit_device.argtypes = fit_args
     lib.pb200_fit_device.restype = C.c_int
@@ -145,6 +147,14 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._lib.pb200_launch_count(self._h))
+
+    def last_fit_variant_counts(self):
+        """(4, 8) int32: series of the last fit per kernel variant (planes, rotation, week table, day table)
+        x seasonality mask."""
+        import numpy as np
+        out = np.zeros(32, np.int32)
+        check(self._lib.pb200_last_fit_variant_counts(self._h, out.ctypes.data), "pb200_last_fit_variant_counts")
+        return out.reshape(4, 8)
 
     def synchronize(self) -> None:
         check(self._lib.pb200_synchronize(self._h), "pb200_synchronize")

@@ -98,12 +98,14 @@ struct pb200_ctx {
     DevBuf d_planes; // fit kernel planes workspace (one slice per resident CTA)
     int lc_max[NLC];
     bool lc_auto = true;   // false when PB200_LC*_MAX pins the CTA width
+    bool tab_on = true;    // PB200_NO_TAB=1 disables the seasonal-table variant (A/B runs)
 };
 
 namespace {
 
 using pb200::FitArgs;
 using pb200::FitOptsDev;
+using pb200::NQ;
 
 typedef cudaError_t (*launch_fn)(int, int, int, const FitArgs&, int, size_t, cudaStream_t, int*);
 const launch_fn LAUNCH[8] = {pb200::launch_fit_mask0, pb200::launch_fit_mask1, pb200::launch_fit_mask2,
@@ -240,6 +242,7 @@ PB200_API pb200_ctx* pb200_create(int device) {
     c->lc_max[1] = env_int("PB200_LC1_MAX", 1 << 30);
     c->lc_max[2] = 1 << 30;
     c->lc_auto = !(getenv("PB200_LC0_MAX") || getenv("PB200_LC1_MAX"));
+    c->tab_on = env_int("PB200_NO_TAB", 0) == 0;
     return c;
 }
 
@@ -259,6 +262,20 @@ PB200_API void pb200_destroy(pb200_ctx* c) {
 
 PB200_API void* pb200_stream(pb200_ctx* c) { return c ? (void*)c->stream : nullptr; }
 PB200_API int64_t pb200_launch_count(pb200_ctx* c) { return c ? c->launches : 0; }
+
+PB200_API int pb200_last_fit_variant_counts(pb200_ctx* c, int32_t* h_counts) {
+    if (!c || !h_counts) return fail(PB200_E_ARG, "null argument");
+    static_assert(PB200_N_VARIANT_COUNTS == NQ, "variant count layout");
+    for (int i = 0; i < NQ; ++i) h_counts[i] = 0;
+    if (!c->d_qctl.p) return PB200_OK;        // no fit yet
+    CK(cudaSetDevice(c->device));
+    int32_t tmp[NLC * NQ];
+    CK(cudaMemcpyAsync(tmp, c->d_qctl.p, sizeof(tmp), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int lc = 0; lc < NLC; ++lc)
+        for (int i = 0; i < NQ; ++i) h_counts[i] += tmp[lc * NQ + i];
+    return PB200_OK;
+}
 
 PB200_API int pb200_synchronize(pb200_ctx* c) {
     if (!c) return fail(PB200_E_ARG, "ctx is null");
@@ -329,18 +346,18 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     CK(c->d_offsets.reserve((size_t)(N + 1) * 8));
     CK(c->d_order.reserve((size_t)N * 4));
     CK(c->d_lenclass.reserve((size_t)N * 4));
-    CK(c->d_qitems.reserve((size_t)NLC * 16 * N * 4));
-    CK(c->d_qctl.reserve((size_t)NLC * 16 * 2 * 4));
+    CK(c->d_qitems.reserve((size_t)NLC * NQ * N * 4));
+    CK(c->d_qctl.reserve((size_t)NLC * NQ * 2 * 4));
     CK(cudaMemcpyAsync(c->d_offsets.p, ho, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_order.p, horder, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_lenclass.p, hlc, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ctl_ev, c->stream));
     c->ctl_pending = true;
-    CK(cudaMemsetAsync(c->d_qctl.p, 0, (size_t)NLC * 16 * 2 * 4, c->stream));
+    CK(cudaMemsetAsync(c->d_qctl.p, 0, (size_t)NLC * NQ * 2 * 4, c->stream));
     CK(cudaMemsetAsync(d_params, 0, (size_t)N * L.pstride * 8, c->stream));
     CK(cudaMemsetAsync(d_tchange, 0, (size_t)N * L.smax * 8, c->stream));
     int* q_count = (int*)c->d_qctl.p;
-    int* q_head = q_count + NLC * 16;
+    int* q_head = q_count + NLC * NQ;
 
     const FitOptsDev od = to_dev(opts);
     // ---- prep kernel ----
@@ -362,6 +379,9 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         pa.q_items = (int*)c->d_qitems.p;
         pa.q_count = q_count;
         pa.o = od;
+        pa.tab_lc_mask = 0;
+        for (int lc = 0; lc < NLC; ++lc)
+            if (c->tab_on && LC_NT[lc] == 32) pa.tab_lc_mask |= 1 << lc;
         const int warps_per_block = 8;
         int grid = (N + warps_per_block - 1) / warps_per_block;
         grid = std::min(grid, c->sms * 8);
@@ -372,25 +392,27 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     // ---- fit kernels: one persistent launch per (length class, seasonality class) ----
     // pass 1: launch geometry and the planes workspace (one slice per resident CTA)
     struct Geo { int grid, Tp, ppad; size_t smem, slice, off; bool on; };
-    Geo geo[NLC][16];       // [length class][regular-grid variant * 8 + seasonality class]
+    Geo geo[NLC][NQ];       // [length class][variant * 8 + seasonality class]
     size_t planes_bytes = 0;
     for (int lc = 0; lc < NLC; ++lc)
-        for (int rm = 0; rm < 16; ++rm) {
+        for (int rm = 0; rm < NQ; ++rm) {
             const int mask = rm & 7, reg = rm >> 3;
             Geo& g = geo[lc][rm];
             g.on = false;
             if (lc_n[lc] == 0) continue;
             if (reg && mask == 0) continue;       // no Fourier features: nothing to regenerate
+            if (reg >= 2 && (mask != 6 || LC_NT[lc] != 32 || !c->tab_on)) continue;   // seasonal-table variants
             auto impossible = [&](int bit, int sw) { return (sw == 0 && (mask & bit)) || (sw == 1 && !(mask & bit)); };
             if (impossible(1, opts->yearly) || impossible(2, opts->weekly) || impossible(4, opts->daily)) continue;
             const int NT = LC_NT[lc];
             const int chunk = std::max((lc_tmax[lc] + NT - 1) / NT, 1);
-            g.Tp = ((lc_tmax[lc] + chunk + 7) / 8) * 8;
+            g.Tp = ((lc_tmax[lc] + chunk + pb200::TAB_CHUNK_SLACK + 1 + 7) / 8) * 8;   // the table variants may widen a chunk
             const int K = mask_k(mask);
             g.ppad = ((L.smax + (K > 0 ? K : 1) + 3) + 1) & ~1;
             const int nst = reg ? 0 : mask_nseas(mask);                    // stored feature planes
             const int nsa = (mask & 1) + ((mask >> 1) & 1) + ((mask >> 2) & 1);   // active seasonalities
-            g.smem = pb200::fit_smem_bytes(NT, 1 + nst, g.ppad, reg ? nsa : 0);
+            g.smem = pb200::fit_smem_bytes(NT, 1 + nst, g.ppad, reg == 1 ? nsa : (reg == 2 ? 1 : (reg == 3 ? 2 : 0)),
+                                           reg == 2 ? pb200::PTAB_WEEK_MAX : (reg == 3 ? pb200::PTAB_DAY_MAX : 0));
             int occ = 0;
             FitArgs dummy{};
             CK(LAUNCH[mask](NT, opts->growth, reg, dummy, 0, g.smem, c->stream, &occ));
@@ -405,7 +427,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     for (int lc = 0; lc < NLC; ++lc) {
         if (lc_n[lc] == 0) continue;
         const int NT = LC_NT[lc];
-        for (int rm = 0; rm < 16; ++rm) {
+        for (int rm = 0; rm < NQ; ++rm) {
             const int mask = rm & 7, reg = rm >> 3;
             const Geo& g = geo[lc][rm];
             if (!g.on) continue;
@@ -416,7 +438,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             fa.y = d_y;
             fa.y_dtype = y_dtype;
             fa.offsets = (const long long*)c->d_offsets.p;
-            const int q = lc * 16 + rm;
+            const int q = lc * NQ + rm;
             fa.q_items = (const int*)c->d_qitems.p + (size_t)q * N;
             fa.q_count = q_count + q;
             fa.q_head = q_head + q;

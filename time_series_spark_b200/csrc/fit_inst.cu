@@ -15,7 +15,7 @@ constexpr int YO = (PB200_MASK & 1) ? 10 : 0;
 constexpr int WO = (PB200_MASK & 2) ? 3 : 0;
 constexpr int DO = (PB200_MASK & 4) ? 4 : 0;
 
-template <int NT, bool LOGI, bool REG>
+template <int NT, bool LOGI, int REG>
 static cudaError_t launch_one(const FitArgs& a, int grid, size_t smem, cudaStream_t st, int* occ) {
     auto kern = fit_kernel<NT, LOGI, YO, WO, DO, REG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -33,10 +33,15 @@ static cudaError_t launch_one(const FitArgs& a, int grid, size_t smem, cudaStrea
 
 template <int NT>
 static cudaError_t launch_nt(int logi, int reg, const FitArgs& a, int grid, size_t smem, cudaStream_t st, int* occ) {
-    if constexpr (PB200_MASK != 0) {        // the regular-grid variant only differs when there are Fourier features
-        if (reg) return logi ? launch_one<NT, true, true>(a, grid, smem, st, occ) : launch_one<NT, false, true>(a, grid, smem, st, occ);
+    if constexpr (PB200_MASK == 6 && NT == 32) {   // seasonal-table variants: weekly + daily, warp per series
+        if (reg == 2) return logi ? launch_one<NT, true, 2>(a, grid, smem, st, occ) : launch_one<NT, false, 2>(a, grid, smem, st, occ);
+        if (reg == 3) return logi ? launch_one<NT, true, 3>(a, grid, smem, st, occ) : launch_one<NT, false, 3>(a, grid, smem, st, occ);
     }
-    return logi ? launch_one<NT, true, false>(a, grid, smem, st, occ) : launch_one<NT, false, false>(a, grid, smem, st, occ);
+    if (reg >= 2) return cudaErrorInvalidValue;
+    if constexpr (PB200_MASK != 0) {        // the regular-grid variant only differs when there are Fourier features
+        if (reg) return logi ? launch_one<NT, true, 1>(a, grid, smem, st, occ) : launch_one<NT, false, 1>(a, grid, smem, st, occ);
+    }
+    return logi ? launch_one<NT, true, 0>(a, grid, smem, st, occ) : launch_one<NT, false, 0>(a, grid, smem, st, occ);
 }
 
 cudaError_t PB200_CAT(launch_fit_mask, PB200_MASK)(int nt, int logi, int reg, const FitArgs& a, int grid, size_t smem,
