@@ -369,10 +369,28 @@ def _tab_cases():
     ]
 
 
+_TAB_MODES = {
+    "logistic_multiplicative": ({}, {}),                       # the reference's configuration
+    "linear_multiplicative": ({"growth": "linear"}, {"growth": "linear"}),
+    "logistic_additive": ({"seasonality_mode": "additive"}, {"seasonality_mode": "additive"}),
+}
+
+
+@pytest.mark.parametrize("mode", ["linear_multiplicative", "logistic_additive"])
+@pytest.mark.parametrize("which", ["day_table_15min", "week_table_hourly"])
+def test_table_variants_other_growth_and_mode(warp_ctx, warp_ctx_no_tab, which, mode):
+    case = [c for c in _tab_cases() if c[0] == which][0]
+    _check_table_objective(warp_ctx, warp_ctx_no_tab, case, mode)
+
+
 @pytest.mark.parametrize("case", _tab_cases(), ids=lambda c: c[0])
 def test_table_variants_objective_and_gradient(warp_ctx, warp_ctx_no_tab, case):
+    _check_table_objective(warp_ctx, warp_ctx_no_tab, case, "logistic_multiplicative")
+
+
+def _check_table_objective(warp_ctx, warp_ctx_no_tab, case, mode):
     name, b, variant = case
-    opts, oopts = batched.make_options(), po.ProphetOptions()
+    opts, oopts = batched.make_options(**_TAB_MODES[mode][0]), po.ProphetOptions(**_TAB_MODES[mode][1])
     lay = L.get_layout(opts)
     rng = np.random.RandomState(5)
     thetas, preps = [], []
@@ -399,7 +417,8 @@ def test_table_variants_objective_and_gradient(warp_ctx, warp_ctx_no_tab, case):
         gd = np.max(np.abs(g[i, :t.size] - go)) / max(1.0, np.max(np.abs(go)))
         assert gd <= 1e-8, (name, i, gd)
         # table and rotation variants are the same sums in another order
-        assert abs(f[i] - f0[i]) <= 1e-11 * max(1.0, abs(fo))
+        # (f is a difference of terms of size ~T: 0.5 ss / sigma^2 against T log sigma, so an absolute 1e-10 is 1e-13 of them)
+        assert abs(f[i] - f0[i]) <= 1e-10 * max(1.0, abs(fo))
         assert np.max(np.abs(g[i] - g0[i])) <= 1e-9 * max(1.0, np.max(np.abs(go)))
 
 
