@@ -99,6 +99,7 @@ struct pb200_ctx {
     int lc_max[NLC];
     bool lc_auto = true;   // false when PB200_LC*_MAX pins the CTA width
     bool tab_on = true;    // PB200_NO_TAB=1 disables the seasonal-table variant (A/B runs)
+    bool align_on = false; // PB200_ALIGN=1: experimental phase-aligned 16-engine CTAs for the day-table class (fit_inst_aligned.cu)
 };
 
 namespace {
@@ -106,6 +107,9 @@ namespace {
 using pb200::FitArgs;
 using pb200::FitOptsDev;
 using pb200::NQ;
+
+extern "C" int pb200_launch_fit_aligned(int logi, const void* args, int grid, void* stream, int* occ);   // fit_inst_aligned.cu
+extern "C" int pb200_aligned_geometry(int* engines, int* slice_bytes, int* args_bytes);
 
 typedef cudaError_t (*launch_fn)(int, int, int, const FitArgs&, int, size_t, cudaStream_t, int*);
 const launch_fn LAUNCH[8] = {pb200::launch_fit_mask0, pb200::launch_fit_mask1, pb200::launch_fit_mask2,
@@ -243,6 +247,7 @@ PB200_API pb200_ctx* pb200_create(int device) {
     c->lc_max[2] = 1 << 30;
     c->lc_auto = !(getenv("PB200_LC0_MAX") || getenv("PB200_LC1_MAX"));
     c->tab_on = env_int("PB200_NO_TAB", 0) == 0;
+    c->align_on = env_int("PB200_ALIGN", 0) != 0;
     return c;
 }
 
@@ -391,7 +396,9 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     }
     // ---- fit kernels: one persistent launch per (length class, seasonality class) ----
     // pass 1: launch geometry and the planes workspace (one slice per resident CTA)
-    struct Geo { int grid, Tp, ppad; size_t smem, slice, off; bool on; };
+    struct Geo { int grid, Tp, ppad; size_t smem, slice, off; bool on, aligned; };
+    int al_engines = 0, al_slice = 0, al_args = 0;
+    pb200_aligned_geometry(&al_engines, &al_slice, &al_args);
     Geo geo[NLC][NQ];       // [length class][variant * 8 + seasonality class]
     size_t planes_bytes = 0;
     for (int lc = 0; lc < NLC; ++lc)
@@ -399,6 +406,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             const int mask = rm & 7, reg = rm >> 3;
             Geo& g = geo[lc][rm];
             g.on = false;
+            g.aligned = false;
             if (lc_n[lc] == 0) continue;
             if (reg && mask == 0) continue;       // no Fourier features: nothing to regenerate
             if (reg >= 2 && (mask != 6 || LC_NT[lc] != 32 || !c->tab_on)) continue;   // seasonal-table variants
@@ -415,11 +423,21 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
                                            reg == 2 ? pb200::PTAB_WEEK_MAX : (reg == 3 ? pb200::PTAB_DAY_MAX : 0));
             int occ = 0;
             FitArgs dummy{};
+            g.slice = (size_t)(1 + nst) * g.Tp;                   // double2 elements
+            g.off = planes_bytes;
+            if (reg == 3 && c->align_on && g.smem <= (size_t)al_slice && al_args == (int)sizeof(FitArgs)) {
+                // experimental: CTAs of al_engines phase-aligned one-warp engines (one planes slice per engine)
+                if (pb200_launch_fit_aligned(opts->growth, &dummy, 0, c->stream, &occ) != 0 || occ < 1)
+                    return fail(PB200_E_UNSUPPORTED, "aligned fit kernel does not fit on an SM");
+                g.aligned = true;
+                g.grid = (int)std::min<int64_t>(((int64_t)lc_n[lc] + al_engines - 1) / al_engines, (int64_t)c->sms * occ);
+                planes_bytes += (size_t)g.grid * al_engines * g.slice * 16;
+                g.on = true;
+                continue;
+            }
             CK(LAUNCH[mask](NT, opts->growth, reg, dummy, 0, g.smem, c->stream, &occ));
             if (occ < 1) return fail(PB200_E_UNSUPPORTED, "fit kernel does not fit on an SM");
             g.grid = (int)std::min<int64_t>((int64_t)lc_n[lc], (int64_t)c->sms * occ);
-            g.slice = (size_t)(1 + nst) * g.Tp;                   // double2 elements
-            g.off = planes_bytes;
             planes_bytes += (size_t)g.grid * g.slice * 16;
             g.on = true;
         }
@@ -457,7 +475,12 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             fa.theta_in = d_theta_in;
             fa.grad_out = d_grad_out;
             fa.o = od;
-            CK(LAUNCH[mask](NT, opts->growth, reg, fa, g.grid, smem, c->stream, nullptr));
+            if (g.aligned) {
+                if (pb200_launch_fit_aligned(opts->growth, &fa, g.grid, c->stream, nullptr) != 0)
+                    return fail(PB200_E_CUDA, "aligned fit kernel launch", cudaGetLastError());
+            } else {
+                CK(LAUNCH[mask](NT, opts->growth, reg, fa, g.grid, smem, c->stream, nullptr));
+            }
             c->launches++;
         }
     }
