@@ -133,6 +133,11 @@ PB200_API int64_t pb200_launch_count(pb200_ctx* ctx);
  * counts[v*8 + mask], summed over the CTA-width classes; v = 0 feature planes, 1 regular-grid rotation,
  * 2 week-period seasonal table, 3 day-period seasonal table; mask = bit0 yearly | bit1 weekly |
  * bit2 daily.  Synchronises the context's stream. */
+/* Diagnostics (host arithmetic, no GPU needed): points per lane the seasonal-table kernel variants give a
+ * series of T points whose table period is P grid steps -- the smallest chunk >= ceil(T / 32) for which the 64
+ * residual bins the 32 lanes update in one loop step are pairwise distinct (what makes those updates race-free
+ * and deterministic) -- or -1 if there is none within the slack the planes workspace allows. */
+PB200_API int32_t pb200_tab_chunk(int32_t T, int32_t P);
 #define PB200_N_VARIANT_COUNTS 32
 PB200_API int pb200_last_fit_variant_counts(pb200_ctx* ctx, int32_t* h_counts);
 

@@ -172,3 +172,29 @@ def test_no_cpu_fallback_without_a_gpu():
         pytest.skip("GPU present")
     with pytest.raises(L.Pb200Error):
         L.Context(0)
+
+
+def test_tab_chunk_gives_conflict_free_bins():
+    """Host arithmetic behind the seasonal-table fit-kernel variants (csrc/fit_kernel.cuh tab_chunk /
+    point_pass_tab): lane l owns points [l*chunk, (l+1)*chunk) and in loop step m updates the residual bins
+    (l*chunk + 2m) % P and (l*chunk + 2m + 1) % P without atomics -- valid only if those 64 bins are pairwise
+    distinct in every step.  Checked exhaustively for the table periods the variants accept."""
+    lib = L.load()
+    slack = 12                                              # TAB_CHUNK_SLACK: what the planes workspace allows for
+    lanes = np.arange(32)
+    for P in range(64, 169):
+        for T in list(range(2 * P + 1, 2 * P + 70)) + [1440, 1400, 2016, 4321, 10080, 43200]:
+            c = lib.pb200_tab_chunk(T, P)
+            c0 = -(-T // 32)
+            if c < 0:
+                continue                                    # no chunk within the slack: prep_kernel keeps the rotation variant
+            assert c0 <= c <= c0 + slack
+            assert -(-T // c) <= 32                         # still at most 32 active lanes
+            for m in (0, 1, c // 2):                        # bins are a rigid shift of step 0's: three steps suffice
+                bins = np.concatenate([(lanes * c + 2 * m) % P, (lanes * c + 2 * m + 1) % P])
+                assert np.unique(bins).size == 64, (P, T, c, m)
+    # the bench workload and the hourly case get a chunk, and it is the documented one
+    assert lib.pb200_tab_chunk(1440, 96) == 45
+    assert lib.pb200_tab_chunk(1400, 96) == 45              # 44 would collide
+    assert lib.pb200_tab_chunk(1440, 168) > 0
+    assert lib.pb200_tab_chunk(1440, 65) == -1 or lib.pb200_tab_chunk(1440, 65) >= 45

@@ -44,7 +44,7 @@ class Layout(C.Structure):
 
 EXPORTS = [
     "pb200_default_options", "pb200_get_layout", "pb200_create", "pb200_destroy", "pb200_last_error",
-    "pb200_stream", "pb200_launch_count", "pb200_last_fit_variant_counts", "pb200_fit_device", "pb200_fit_host", "pb200_predict_device",
+    "pb200_stream", "pb200_launch_count", "pb200_last_fit_variant_counts", "pb200_tab_chunk", "pb200_fit_device", "pb200_fit_host", "pb200_predict_device",
     "pb200_predict_host", "pb200_make_future_device", "pb200_synchronize", "pb200_objective_host",
 ]
 
@@ -77,6 +77,8 @@ def load() -> C.CDLL:
     lib.pb200_stream.restype = vp
     lib.pb200_launch_count.argtypes = [vp]
     lib.pb200_launch_count.restype = i64
+    lib.pb200_tab_chunk.argtypes = [i32, i32]
+    lib.pb200_tab_chunk.restype = i32
     lib.pb200_last_fit_variant_counts.argtypes = [vp, vp]
     lib.pb200_last_fit_variant_counts.restype = C.c_int
     fit_args = [vp, OP, vp, vp, i32, vp, i64, dbl, dbl, vp, vp, vp, vp, vp, vp]

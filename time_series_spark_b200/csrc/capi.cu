@@ -268,6 +268,11 @@ PB200_API void pb200_destroy(pb200_ctx* c) {
 PB200_API void* pb200_stream(pb200_ctx* c) { return c ? (void*)c->stream : nullptr; }
 PB200_API int64_t pb200_launch_count(pb200_ctx* c) { return c ? c->launches : 0; }
 
+PB200_API int32_t pb200_tab_chunk(int32_t T, int32_t P) {
+    if (T < 1 || P < 2) return -1;
+    return pb200::tab_chunk(T, P);
+}
+
 PB200_API int pb200_last_fit_variant_counts(pb200_ctx* c, int32_t* h_counts) {
     if (!c || !h_counts) return fail(PB200_E_ARG, "null argument");
     static_assert(PB200_N_VARIANT_COUNTS == NQ, "variant count layout");
