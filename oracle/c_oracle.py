@@ -16,7 +16,10 @@ class COpts(C.Structure):
                 ("changepoint_range", C.c_double), ("tau", C.c_double), ("seas_prior", C.c_double),
                 ("yearly", C.c_int), ("weekly", C.c_int), ("daily", C.c_int), ("max_iter", C.c_int),
                 ("init_alpha", C.c_double), ("tol_obj", C.c_double), ("tol_rel_obj", C.c_double),
-                ("tol_grad", C.c_double), ("tol_rel_grad", C.c_double), ("tol_param", C.c_double)]
+                ("tol_grad", C.c_double), ("tol_rel_grad", C.c_double), ("tol_param", C.c_double),
+                ("algorithm", C.c_int), ("reserved", C.c_int)]
+
+ALG_LBFGS_NEWTON, ALG_LBFGS, ALG_NEWTON = 0, 1, 2
 
 
 def load():
@@ -24,6 +27,7 @@ def load():
     if _lib is None:
         _lib = C.CDLL(build_oracle.build())
         _lib.po_fit_batch.restype = C.c_int
+        _lib.po_fit_batch_trace.restype = C.c_int
         _lib.po_objective.restype = C.c_int
     return _lib
 
@@ -37,7 +41,10 @@ def options(growth="logistic", seasonality_mode="multiplicative", yearly=-1, wee
     return o
 
 
-def fit_batch(ds, y, offsets, floor=0.0, cap_multiplier=1.1, opts: COpts | None = None, nthreads: int = 0, pstride: int = 96):
+def fit_batch(ds, y, offsets, floor=0.0, cap_multiplier=1.1, opts: COpts | None = None, nthreads: int = 0, pstride: int = 96,
+              trace_cap: int = 0):
+    """Returns (theta, f, info) -- and a 4th array [n, trace_cap, 4] of (iteration, f_k, alpha_k, n_evals) rows per
+    accepted L-BFGS iteration when ``trace_cap`` > 0."""
     opts = opts or options()
     ds = np.ascontiguousarray(ds, dtype=np.int64)
     y = np.ascontiguousarray(y, dtype=np.float64)
@@ -46,9 +53,13 @@ def fit_batch(ds, y, offsets, floor=0.0, cap_multiplier=1.1, opts: COpts | None 
     theta = np.zeros((n, pstride))
     f = np.zeros(n)
     info = np.zeros((n, 5), np.int32)
-    load().po_fit_batch(C.c_void_p(ds.ctypes.data), C.c_void_p(y.ctypes.data), C.c_void_p(offsets.ctypes.data), C.c_int(n),
-                        C.c_double(floor), C.c_double(cap_multiplier), C.byref(opts), C.c_void_p(theta.ctypes.data),
-                        C.c_int(pstride), C.c_void_p(f.ctypes.data), C.c_void_p(info.ctypes.data), C.c_int(nthreads))
+    trace = np.zeros((n, trace_cap, 4)) if trace_cap > 0 else None
+    load().po_fit_batch_trace(C.c_void_p(ds.ctypes.data), C.c_void_p(y.ctypes.data), C.c_void_p(offsets.ctypes.data), C.c_int(n),
+                              C.c_double(floor), C.c_double(cap_multiplier), C.byref(opts), C.c_void_p(theta.ctypes.data),
+                              C.c_int(pstride), C.c_void_p(f.ctypes.data), C.c_void_p(info.ctypes.data), C.c_int(nthreads),
+                              C.c_void_p(trace.ctypes.data if trace is not None else None), C.c_int(trace_cap))
+    if trace is not None:
+        return theta, f, info, trace
     return theta, f, info     # info columns: status, iters, n_evals, S, K
 
 

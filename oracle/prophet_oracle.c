@@ -18,6 +18,9 @@
  *                   GPU kernel uses, so the CPU baseline is not handicapped.
  *   po_lbfgs        stan/optimization/bfgs.hpp BFGSMinimizer::step + lbfgs_update.hpp +
  *                   bfgs_linesearch.hpp (WolfeLineSearch, WolfLSZoom, CubicInterp)
+ *   po_newton       stan/services/optimize/newton.hpp + stan/optimization/newton.hpp (newton_step,
+ *                   make_negative_definite_and_solve) + stan/model/grad_hess_log_prob.hpp -- what
+ *                   fbprophet 0.5's fit() falls back to when PyStan raises on a line-search failure
  *   po_fit_batch    the per-group loop Spark runs (one group per task, prophet_modeler.py:139-141),
  *                   here an OpenMP loop over series on the host cores.
  */
@@ -42,6 +45,8 @@ typedef struct {
     int yearly, weekly, daily;      /* -1 auto, 0 off, 1 on */
     int max_iter;
     double init_alpha, tol_obj, tol_rel_obj, tol_grad, tol_rel_grad, tol_param;
+    int algorithm;       /* 0 L-BFGS, Newton retry on line-search failure (fbprophet 0.5 fit()); 1 L-BFGS only; 2 Newton only */
+    int reserved;
 } po_opts;
 
 typedef struct {
@@ -58,7 +63,7 @@ static void po_default(po_opts* o) {
     o->growth = 1; o->multiplicative = 1; o->n_changepoints = 25; o->changepoint_range = 0.8;
     o->tau = 0.05; o->seas_prior = 10.0; o->yearly = o->weekly = o->daily = -1; o->max_iter = 10000;
     o->init_alpha = 1e-3; o->tol_obj = 1e-12; o->tol_rel_obj = 1e4; o->tol_grad = 1e-8;
-    o->tol_rel_grad = 1e7; o->tol_param = 1e-8;
+    o->tol_rel_grad = 1e7; o->tol_param = 1e-8; o->algorithm = 0; o->reserved = 0;
 }
 
 void po_default_options(po_opts* o) { po_default(o); }
@@ -272,7 +277,8 @@ static double cubic_interp(double df0, double x1, double f1, double df1, double 
 }
 
 /* returns Stan termination code; x holds the result */
-static int po_lbfgs(const po_prep* p, const po_opts* o, double* x, double* f_final, int* iters_out, int* nevals_out) {
+static int po_lbfgs(const po_prep* p, const po_opts* o, double* x, double* f_final, int* iters_out, int* nevals_out,
+                    double* trace, int trace_cap) {
     const int P = p->S + p->K + 3;
     const double eps = 2.220446049250313e-16;
     const double c1 = 1e-4, c2 = 0.9, minAlpha = 1e-12;
@@ -359,6 +365,10 @@ static int po_lbfgs(const po_prep* p, const po_opts* o, double* x, double* f_fin
         memcpy(xprev, x, sizeof(double) * P); memcpy(gprev, g, sizeof(double) * P); memcpy(pp, pk, sizeof(double) * P);
         memcpy(x, xt, sizeof(double) * P); memcpy(g, gt, sizeof(double) * P);
         fk_1 = fk; fk = ft;
+        if (trace && it <= trace_cap) {     /* row it-1: iteration, f_k, alpha_k, evaluations so far */
+            double* tr = trace + (size_t)(it - 1) * 4;
+            tr[0] = (double)it; tr[1] = fk; tr[2] = alpha; tr[3] = (double)nev;
+        }
         if (resetB) { hn = 0; hhead = 0; }
         int slot;
         if (hn < PO_HIST) { slot = (hhead + hn) % PO_HIST; ++hn; } else { slot = hhead; hhead = (hhead + 1) % PO_HIST; }
@@ -398,6 +408,91 @@ static int po_lbfgs(const po_prep* p, const po_opts* o, double* x, double* f_fin
     }
 }
 
+
+/* ---- Newton fallback (stan::optimization::newton_step and what it calls) ---- */
+
+/* eigen-decomposition of the symmetric n x n matrix A (row-major, destroyed) by cyclic Jacobi rotations:
+ * on return the diagonal of A holds the eigenvalues and the COLUMNS of V the eigenvectors */
+static void po_jacobi(double* A, double* V, int n) {
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) V[i * n + j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; ++i) { diag += A[i * n + i] * A[i * n + i]; for (int j = i + 1; j < n; ++j) off += A[i * n + j] * A[i * n + j]; }
+        if (off <= 1e-30 * diag || off == 0.0) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * n + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s_ = t * c;
+                for (int k = 0; k < n; ++k) {      /* columns p, q of A and V */
+                    const double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s_ * akq; A[k * n + q] = s_ * akp + c * akq;
+                    const double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - s_ * vkq; V[k * n + q] = s_ * vkp + c * vkq;
+                }
+                for (int k = 0; k < n; ++k) {      /* rows p, q of A */
+                    const double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s_ * aqk; A[q * n + k] = s_ * apk + c * aqk;
+                }
+            }
+    }
+}
+
+/* returns a Stan-style status: 60 = model from the Newton run, -1 = an evaluation inside grad_hess_log_prob failed
+ * (Stan throws; PyStan raises RuntimeError a second time and the reference UDF drops the series) */
+static int po_newton(const po_prep* p, const po_opts* o, double* x, double* f_final, int* iters_out, int* nevals_out) {
+    const int P = p->S + p->K + 3;
+    const double eps = 1e-3, pert[4] = {-2 * eps, -eps, eps, 2 * eps}, coef[4] = {1.0 / 12.0, -2.0 / 3.0, 2.0 / 3.0, -1.0 / 12.0};
+    const double half_inv_eps = 0.5 / eps;   /* see the note in prophet_oracle.py::_grad_hess on Stan's half_epsilon */
+    double* H = (double*)malloc(sizeof(double) * P * P * 2);
+    double* V = H + P * P;
+    double g[PO_MAXP], gi[PO_MAXP], xp[PO_MAXP], u[PO_MAXP], w[PO_MAXP], xn[PO_MAXP];
+    int nev = 0, it = 0, st = 60;
+    double f, ftmp;
+    int err = po_eval(p, x, &f, g); ++nev;
+    if (err) f = INFINITY;
+    for (it = 1; it <= o->max_iter; ++it) {
+        double f0;
+        err = po_eval(p, x, &f0, g); ++nev;
+        if (err) { st = -1; break; }
+        for (int q = 0; q < P * P; ++q) H[q] = 0.0;
+        memcpy(xp, x, sizeof(double) * P);
+        for (int d = 0; d < P && st == 60; ++d) {
+            for (int i = 0; i < 4; ++i) {
+                xp[d] = x[d] + pert[i];
+                err = po_eval(p, xp, &ftmp, gi); ++nev;
+                if (err) { st = -1; break; }
+                for (int dd = 0; dd < P; ++dd) { const double inc = half_inv_eps * coef[i] * gi[dd]; H[d * P + dd] += inc; H[dd * P + d] += inc; }
+            }
+            xp[d] = x[d];
+        }
+        if (st != 60) break;
+        po_jacobi(H, V, P);
+        for (int j = 0; j < P; ++j) { double s_ = 0.0; for (int k = 0; k < P; ++k) s_ += V[k * P + j] * g[k]; w[j] = s_ / fabs(H[j * P + j]); }
+        for (int k = 0; k < P; ++k) { double s_ = 0.0; for (int j = 0; j < P; ++j) s_ += V[k * P + j] * w[j]; u[k] = s_; }
+        double step = 2.0, f1 = INFINITY;
+        int moved = 0;
+        for (;;) {
+            step *= 0.5;
+            if (step < 1e-50) break;
+            for (int q = 0; q < P; ++q) xn[q] = x[q] - step * u[q];
+            err = po_eval(p, xn, &f1, gi); ++nev;
+            if (err || !(f1 <= f0)) continue;
+            moved = 1;
+            break;
+        }
+        const double last = f;
+        if (moved) { memcpy(x, xn, sizeof(double) * P); f = f1; } else f = f0;
+        if (it > 1 && fabs(f - last) < 1e-8) break;
+    }
+    if (it > o->max_iter) it = o->max_iter;
+    free(H);
+    *f_final = f; *iters_out = it; *nevals_out = nev;
+    return st;
+}
+
 /* objective + gradient at a caller-supplied theta (for cross-checks); returns err */
 int po_objective(const long long* ds, const double* y, int T, double floor_, double cap, const po_opts* o,
                  const double* theta, double* f, double* g, int* S_out, int* K_out) {
@@ -414,8 +509,9 @@ int po_objective(const long long* ds, const double* y, int T, double floor_, dou
  * Fits n series.  theta_out rows (stride pstride) hold Stan's unconstrained optimum
  * k, m, delta[S], log sigma, beta[K]; info rows: status, iters, n_evals, S, K.
  */
-int po_fit_batch(const long long* ds, const double* y, const long long* offsets, int n, double floor_, double cap_multiplier,
-                 const po_opts* o, double* theta_out, int pstride, double* f_out, int* info, int nthreads) {
+int po_fit_batch_trace(const long long* ds, const double* y, const long long* offsets, int n, double floor_, double cap_multiplier,
+                       const po_opts* o, double* theta_out, int pstride, double* f_out, int* info, int nthreads,
+                       double* trace, int trace_cap) {
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -428,7 +524,16 @@ int po_fit_batch(const long long* ds, const double* y, const long long* offsets,
         po_prep p; double th[PO_MAXP];
         int st = po_prepare(ds + a, y + a, T, floor_, ymax * cap_multiplier, o, &p, th);
         int iters = 0, nev = 0; double f = NAN;
-        if (st == 0) st = po_lbfgs(&p, o, th, &f, &iters, &nev);
+        double th0[PO_MAXP];
+        memcpy(th0, th, sizeof th0);
+        if (st == 0 && o->algorithm != 2) st = po_lbfgs(&p, o, th, &f, &iters, &nev, trace ? trace + (size_t)i * trace_cap * 4 : NULL, trace_cap);
+        if ((st == -1 && o->algorithm == 0) || (st == 0 && o->algorithm == 2)) {
+            /* fbprophet 0.5 fit(): except RuntimeError -> optimizing(init=stan_init, algorithm='Newton') */
+            int it2 = 0, nev2 = 0;
+            memcpy(th, th0, sizeof th0);
+            st = po_newton(&p, o, th, &f, &it2, &nev2);
+            iters += it2; nev += nev2;
+        }
         if (st >= 0 || st == -1 || st == -2) {
             for (int q = 0; q < p.S + p.K + 3 && q < pstride; ++q) theta_out[(size_t)i * pstride + q] = th[q];
             info[i * 5 + 3] = p.S; info[i * 5 + 4] = p.K;
@@ -438,4 +543,9 @@ int po_fit_batch(const long long* ds, const double* y, const long long* offsets,
         f_out[i] = f;
     }
     return 0;
+}
+
+int po_fit_batch(const long long* ds, const double* y, const long long* offsets, int n, double floor_, double cap_multiplier,
+                 const po_opts* o, double* theta_out, int pstride, double* f_out, int* info, int nthreads) {
+    return po_fit_batch_trace(ds, y, offsets, n, floor_, cap_multiplier, o, theta_out, pstride, f_out, info, nthreads, NULL, 0);
 }

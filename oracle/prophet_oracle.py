@@ -121,6 +121,7 @@ class FitResult:
 # Stan TerminationCondition (bfgs.hpp)
 TERM_SUCCESS, TERM_ABSX, TERM_ABSF, TERM_RELF = 0, 10, 20, 21
 TERM_ABSGRAD, TERM_RELGRAD, TERM_MAXIT, TERM_LSFAIL = 30, 31, 40, -1
+TERM_NEWTON = 60     # not a Stan code: the model came from fbprophet's Newton retry (stan_newton below)
 
 
 # --------------------------------------------------------------------------
@@ -332,7 +333,7 @@ def neg_logp_grad(theta: np.ndarray, p: Prepared) -> Tuple[int, float, np.ndarra
             return 1, np.nan, g
         r = p.y - mu
         ss = float(r @ r)
-        inv_s2 = 1.0 / (sigma * sigma)
+        inv_s2 = float(np.float64(1.0) / np.float64(sigma * sigma))   # sigma^2 may underflow to 0: inf, reported as a non-finite objective
         f = (0.5 * ss * inv_s2 + T * u + k * k / 50.0 + m * m / 50.0
              + np.abs(delta).sum() / p.tau + 2.0 * sigma * sigma
              + float(np.sum(beta * beta / (2.0 * p.sigmas ** 2))))
@@ -506,12 +507,14 @@ def _wolfe_line_search(func, alpha, p, x0, f0, g0, c1, c2, min_alpha, max_ls_its
         nits += 1
 
 
-def stan_lbfgs(fun, x0: np.ndarray, opts: ProphetOptions):
+def stan_lbfgs(fun, x0: np.ndarray, opts: ProphetOptions, trace: Optional[list] = None):
     """stan::optimization::BFGSMinimizer<…, LBFGSUpdate>::initialize + step loop as
     driven by stan::services::optimize::lbfgs.  ``fun(x) -> (err, f, g)`` minimised.
 
     Returns (x, f, iters, ret, n_evals).  ret < 0 is what PyStan turns into the
-    RuntimeError fbprophet 0.5 answers with a Newton retry.
+    RuntimeError fbprophet 0.5 answers with a Newton retry.  ``trace`` (a list) receives one
+    ``(iteration, f_k, alpha_k, n_evals)`` tuple per accepted iteration -- the record the GPU
+    kernel's trajectory hook (pb200_fit_trace_host) writes, compared in tests/test_gpu_trajectory.py.
     """
     func = _Counter(fun)
     c1, c2, min_alpha, max_ls_its, max_ls_restarts = 1e-4, 0.9, 1e-12, 20, 10
@@ -547,6 +550,8 @@ def stan_lbfgs(fun, x0: np.ndarray, opts: ProphetOptions):
         # swap: k <- newest
         xk_1, fk_1, gk_1, pk_1 = xk, fk, gk, pk
         xk, fk, gk = xn, fn, gn
+        if trace is not None:
+            trace.append((it, float(fk), float(alpha), func.n))
         sk = xk - xk_1
         yk = gk - gk_1
         grad_norm = float(np.linalg.norm(gk))
@@ -598,12 +603,105 @@ def stan_lbfgs(fun, x0: np.ndarray, opts: ProphetOptions):
 
 
 # --------------------------------------------------------------------------
+# Stan Newton (fbprophet 0.5 fit(): ``except RuntimeError: model.optimizing(..., algorithm='Newton')``)
+# --------------------------------------------------------------------------
+NEWTON_FD_EPS = 1e-3
+
+
+def _grad_hess(func, x: np.ndarray):
+    """stan::model::grad_hess_log_prob<true, false>: analytic gradient plus a Hessian from 4-point
+    central finite differences of GRADIENTS (perturbations -2e, -e, e, 2e with e = 1e-3,
+    coefficients 1/12, -2/3, 2/3, -1/12), accumulated into rows and columns with half weight each
+    (so the result is symmetric).  An evaluation that fails throws in Stan and surfaces in PyStan as
+    RuntimeError -- which the reference UDF turns into a dropped series (prophet_modeler.py:81-85).
+
+    [UPSTREAM-RECALL, unsure] Stan 2.19's source writes the increment as
+    ``half_epsilon * coefficients[i] * temp_grad[dd]`` with ``half_epsilon = 0.5 * epsilon``; read
+    literally that scales the Hessian by epsilon^2.  The derivative the stencil computes needs
+    ``0.5 / epsilon``, which is what is used here (and in the C port and the GPU kernel).  Only the
+    length of the Newton direction depends on it -- newton_step's step halving absorbs a wrong scale,
+    and the iteration stops on |delta lp| < 1e-8, i.e. at the same optimum either way."""
+    n = x.size
+    err, f, g = func(x)
+    if err:
+        raise RuntimeError("grad_hess_log_prob: error evaluating the log probability")
+    H = np.zeros((n, n))
+    pert = (-2 * NEWTON_FD_EPS, -NEWTON_FD_EPS, NEWTON_FD_EPS, 2 * NEWTON_FD_EPS)
+    coef = (1.0 / 12.0, -2.0 / 3.0, 2.0 / 3.0, -1.0 / 12.0)
+    half_inv_eps = 0.5 / NEWTON_FD_EPS
+    xp = x.copy()
+    for d in range(n):
+        for pe, co in zip(pert, coef):
+            xp[d] = x[d] + pe
+            e2, _, gi = func(xp)
+            if e2:
+                raise RuntimeError("grad_hess_log_prob: error evaluating a perturbed gradient")
+            inc = half_inv_eps * co * gi
+            H[d, :] += inc
+            H[:, d] += inc
+        xp[d] = x[d]
+    return f, g, H
+
+
+def _abs_hessian_solve(H: np.ndarray, g: np.ndarray) -> np.ndarray:
+    """stan::optimization::make_negative_definite_and_solve, in terms of f = -lp: every eigenvalue
+    of the Hessian is replaced by its absolute value before solving, u = V diag(1/|lambda|) V' g."""
+    lam, V = np.linalg.eigh(H)
+    with np.errstate(all="ignore"):
+        return V @ ((V.T @ g) / np.abs(lam))
+
+
+def stan_newton(fun, x0: np.ndarray, opts: ProphetOptions):
+    """stan::services::optimize::newton + stan::optimization::newton_step (Stan 2.19), minimising
+    f = -lp.  Each iteration: gradient and finite-difference Hessian at x, Newton direction with
+    |H|, then step sizes 1, 1/2, 1/4, ... until f does not increase (an evaluation error counts as
+    an increase; below 1e-50 the iteration returns the old point).  Stops when an iteration changes
+    lp by less than 1e-8 (absolute) or after ``iter`` (fbprophet passes 1e4) iterations.  The first
+    comparison in Stan is against lp computed WITH the normalising constants (log_prob<false,false>)
+    while newton_step returns the propto value, so it cannot fire on iteration 1; neither does it here.
+
+    Returns (x, f, iters, ret, n_evals) with ret = TERM_NEWTON; raises RuntimeError where Stan throws."""
+    func = _Counter(fun)
+    x = np.array(x0, dtype=np.float64)
+    err, f, _ = func(x)
+    if err:
+        f = math.inf           # services::newton catches this and carries on with lp = -inf
+    it = 0
+    for it in range(1, opts.max_iter + 1):
+        f0, g, H = _grad_hess(func, x)
+        u = _abs_hessian_solve(H, g)
+        step, f1, xn = 2.0, math.inf, x
+        moved = False
+        while True:
+            step *= 0.5
+            if step < 1e-50:
+                break
+            xn = x - step * u
+            e1, f1, _ = func(xn)
+            if e1 or not (f1 <= f0):
+                continue
+            moved = True
+            break
+        last = f
+        if moved:
+            x, f = xn, f1
+        else:
+            f = f0
+        if it > 1 and abs(f - last) < 1e-8:
+            break
+    return x, float(f), it, TERM_NEWTON, func.n
+
+
+# --------------------------------------------------------------------------
 # fit / predict
 # --------------------------------------------------------------------------
 def fit(ds_ns, y, floor: float = 0.0, cap: Optional[float] = None,
-        opts: Optional[ProphetOptions] = None, cap_multiplier: float = 1.1) -> FitResult:
+        opts: Optional[ProphetOptions] = None, cap_multiplier: float = 1.1,
+        algorithm: str = "LBFGS+Newton", trace: Optional[list] = None) -> FitResult:
     """model_time_series_udf body (prophet_modeler.py:56-66): cap = max(y)*cap_multiplier,
-    then Prophet(...).fit."""
+    then Prophet(...).fit.  ``algorithm``: "LBFGS+Newton" is fbprophet 0.5's fit() -- L-BFGS, and on
+    PyStan's RuntimeError (line-search failure) a Newton run from the same initial point; "LBFGS" /
+    "Newton" run one of them alone (tests)."""
     opts = opts or ProphetOptions()
     ds_ns = np.asarray(ds_ns, dtype=np.int64)
     y = np.asarray(y, dtype=np.float64)
@@ -615,7 +713,14 @@ def fit(ds_ns, y, floor: float = 0.0, cap: Optional[float] = None,
         th, f, it, ret, ne = th0.copy(), float("nan"), 0, TERM_SUCCESS, 0
         sigma = 1e-9
     else:
-        th, f, it, ret, ne = stan_lbfgs(lambda x: neg_logp_grad(x, p), th0, opts)
+        fun = lambda x: neg_logp_grad(x, p)     # noqa: E731
+        if algorithm == "Newton":
+            th, f, it, ret, ne = stan_newton(fun, th0, opts)
+        else:
+            th, f, it, ret, ne = stan_lbfgs(fun, th0, opts, trace=trace)
+            if ret == TERM_LSFAIL and algorithm == "LBFGS+Newton":
+                th, f, it2, ret, ne2 = stan_newton(fun, th0, opts)
+                it, ne = it + it2, ne + ne2
         sigma = math.exp(th[2 + p.S])
     S = p.S
     k, m, delta, beta = th[0], th[1], th[2:2 + S].copy(), th[3 + S:].copy()
