@@ -48,6 +48,11 @@ extern "C" {
 
 /* per-series status (status[] output of fit).  >= 0 : Stan L-BFGS TerminationCondition
  * (stan/optimization/bfgs.hpp), a model row is produced;  < 0 : no model row. */
+/* pb200_options.algorithm */
+#define PB200_ALG_LBFGS_NEWTON 0  /* optimizing(LBFGS); except RuntimeError: optimizing(Newton)  -- fbprophet 0.5 Prophet.fit */
+#define PB200_ALG_LBFGS        1  /* L-BFGS only: a line-search failure is final (status PB200_ST_LSFAIL, row dropped) */
+#define PB200_ALG_NEWTON       2  /* Newton only (tests; later fbprophet versions use it for short histories) */
+
 #define PB200_ST_SUCCESS      0   /* only transient; never final */
 #define PB200_ST_ABSX        10
 #define PB200_ST_ABSF        20
@@ -56,6 +61,7 @@ extern "C" {
 #define PB200_ST_RELGRAD     31
 #define PB200_ST_MAXIT       40
 #define PB200_ST_CONST_LINEAR 50  /* fbprophet "nothing to fit" shortcut: params = init, sigma_obs = 1e-9 */
+#define PB200_ST_NEWTON      60   /* model from fbprophet 0.5's Newton retry after an L-BFGS line-search failure */
 #define PB200_ST_LSFAIL      -1   /* line search failed (PyStan raises RuntimeError -> fbprophet Newton retry) */
 #define PB200_ST_INIT_ERROR  -2   /* objective not finite at the initial point */
 #define PB200_ST_TOO_FEW     -3   /* < 2 rows  (fbprophet ValueError) */
@@ -99,7 +105,7 @@ typedef struct pb200_options {
     double  tol_param;              /* 1e-8 */
     double  interval_width;         /* 0.8 */
     int32_t uncertainty_samples;    /* 1000; 0 = skip yhat_lower / yhat_upper */
-    int32_t reserved;
+    int32_t algorithm;              /* PB200_ALG_*: 0 = fbprophet 0.5's fit(): Stan L-BFGS, Newton retry after a line-search failure */
 } pb200_options;
 
 /* Fills *o with the reference's defaults. */
@@ -191,6 +197,21 @@ PB200_API int pb200_objective_host(pb200_ctx* ctx, const pb200_options* opts,
                    const int64_t* h_offsets, int64_t n_series,
                    double floor, double cap_multiplier, const double* h_theta,
                    double* h_f, double* h_grad, int32_t* h_meta_i32);
+
+/*
+ * Parity-test hook: pb200_fit_host that also records the optimiser's trajectory.  For every accepted
+ * L-BFGS iteration it <= trace_cap of series i, h_trace[(i * trace_cap + it - 1) * 4 ...] =
+ * (it, f_k, alpha_k, objective evaluations so far) -- the record oracle/prophet_oracle.py::stan_lbfgs(trace=...)
+ * produces, so that the two can be compared step by step (a wrong line-search or update constant that still
+ * converges shows up in the first rows).  Rows never written stay 0.
+ */
+PB200_API int pb200_fit_trace_host(pb200_ctx* ctx, const pb200_options* opts,
+                   const int64_t* h_ds, const void* h_y, int32_t y_dtype,
+                   const int64_t* h_offsets, int64_t n_series,
+                   double floor, double cap_multiplier,
+                   double* h_params, double* h_tchange,
+                   int32_t* h_meta_i32, int64_t* h_meta_i64, double* h_meta_f64,
+                   double* h_trace, int32_t trace_cap);
 
 /*
  * Batched predict over `horizon` future timestamps per model.

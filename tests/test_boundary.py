@@ -198,3 +198,53 @@ def test_tab_chunk_gives_conflict_free_bins():
     assert lib.pb200_tab_chunk(1400, 96) == 45              # 44 would collide
     assert lib.pb200_tab_chunk(1440, 168) > 0
     assert lib.pb200_tab_chunk(1440, 65) == -1 or lib.pb200_tab_chunk(1440, 65) >= 45
+
+
+def test_written_forecast_timestamps_look_like_sparks(tmp_path):
+    """Spark's CSV writer prints timestamps as yyyy-MM-dd'T'HH:mm:ss.SSSXXX (reference prophet_scorer.py:147-150
+    relies on that default): 2019-01-01T00:00:05.000Z, not nine fractional digits."""
+    import re as _re
+    tbl = pa.table({"series_id": pa.array([1, 1], pa.int32()), "dim_id": pa.array([2, 2], pa.int32()),
+                    "ds": pa.array([1546300805 * 10**9, 1546301705 * 10**9], pa.int64()).cast(pa.timestamp("ns")),
+                    "yhat": pa.array([5, 6], pa.int32())})
+    scorer = ProphetScorer({"io": {"models": "unused", "forecasts": str(tmp_path / "fc")},
+                            "forecast": {"periods": 2, "frequency": "15min"}})
+    scorer.write_forecasts(scorer.convert_forecasts(Frame(tbl)))
+    lines = open(tmp_path / "fc" / "part-00000.csv").read().strip().split("\n")
+    assert lines[0].replace('"', "") == "created_timestamp,series_id,dim_id,forecast_date,forecast_timestamp,forecast_quantity"
+    f = lines[1].replace('"', "").split(",")
+    assert f[4] == "2019-01-01T00:00:05.000Z" and f[3] == "2019-01-01" and f[5] == "5"
+    assert _re.fullmatch(r"\d{4}-\d\d-\d\dT\d\d:\d\d:\d\d\.\d{3}Z", lines[2].replace('"', "").split(",")[4])
+
+
+def test_rank_local_files_cover_the_input_once(tmp_path):
+    """SURVEY 8e "rank r reads only its row range": the series_id= directories are cut into contiguous,
+    byte-balanced ranges, one per rank; together they are the whole input, pairwise disjoint."""
+    import pyarrow.dataset as pads
+    from time_series_spark_b200.jobs.prophet_modeler import rank_local_files
+    root = tmp_path / "in"
+    sizes = {}
+    for sid in (3, 11, 7, 20, 5, 1):
+        d = root / f"series_id={sid}"
+        d.mkdir(parents=True)
+        rows = 10 * (sid % 4 + 1)
+        (d / "a.csv").write_text("".join(f"{sid},2020-01-01 00:{i % 60:02d}:00,{i}\n" for i in range(rows)))
+        sizes[sid] = (d / "a.csv").stat().st_size
+    part = pads.partitioning(pa.schema([("series_id", pa.int32())]), flavor="hive")
+    dset = pads.dataset(str(root), format="csv", partitioning=part)
+    for ws in (2, 3, 6):
+        got = [rank_local_files(dset, r, ws) for r in range(ws)]
+        flat = [p for g in got for p in g]
+        assert sorted(flat) == sorted(f.path for f in dset.get_fragments()) and len(set(flat)) == len(flat)
+        # contiguous in series_id order
+        ids = [[int(p.split("series_id=")[1].split("/")[0]) for p in g] for g in got]
+        assert sum(ids, []) == sorted(sizes)
+    assert rank_local_files(dset, 0, 7) is None        # fewer directories than ranks: caller shards the groups instead
+
+
+def test_null_group_key_is_refused():
+    from time_series_spark_b200.pack import pack_groups
+    tbl = pa.table({"series_id": pa.array([1, 1], pa.int32()), "dim_id": pa.array([2, None], pa.int32()),
+                    "ds": pa.array([0, 1], pa.int64()).cast(pa.timestamp("ns")), "y": pa.array([1, 2], pa.int32())})
+    with pytest.raises(ValueError, match="null"):
+        pack_groups(tbl, pin=False)

@@ -338,6 +338,22 @@ def warp_ctx():
 
 
 @pytest.fixture(scope="module")
+def warp_ctx_tab32():
+    """One warp per series for the day-table class too (point_pass_tab, the round-1 kernel) instead of the
+    grouped-lanes kernel of fit_group.cuh."""
+    c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def warp_ctx_g16():
+    c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=16)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
 def warp_ctx_no_tab():
     c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_NO_TAB=1)
     yield c
@@ -364,7 +380,8 @@ def _tab_cases():
         ("week_table_hourly", _regrid(c3, H), 2),            # P = 168, 60 days
         ("week_table_hourly_T337", _regrid(c3, H, 337), 2),  # two weeks + 1 point: the shortest series with weekly
         ("week_table_2h", _regrid(c3, 2 * H), 2),            # P = 84, 120 days
-        ("rotation_30min", _regrid(c3, 30 * 60 * 10**9), 1),     # P = 48 < 64 bins: no conflict-free pairing
+        ("day_table_30min", _regrid(c3, 30 * 60 * 10**9), 3),    # P = 48: the smallest table of the grouped kernel
+        ("rotation_10min", _regrid(c3, 10 * 60 * 10**9), 1),     # P = 144 > 96 phases per day: no table
         ("rotation_25min", _regrid(c3, 25 * 60 * 10**9), 1),   # step divides neither day nor week: no table
     ]
 
@@ -422,6 +439,15 @@ def _check_table_objective(warp_ctx, warp_ctx_no_tab, case, mode):
         assert np.max(np.abs(g[i] - g0[i])) <= 1e-9 * max(1.0, np.max(np.abs(go)))
 
 
+@pytest.mark.parametrize("which", ["day_table_15min", "day_table_15min_T1400", "day_table_20min"])
+@pytest.mark.parametrize("kernel", ["tab32", "g16"])
+def test_day_table_other_kernels_objective_and_gradient(warp_ctx_tab32, warp_ctx_g16, warp_ctx_no_tab, which, kernel):
+    """The day-table class on its two other kernels: 16 lanes per series (PB200_GROUP=16) and the one-warp-per-series
+    point_pass_tab (PB200_GROUP=0); the default (8 lanes per series) is what every other test of this section runs."""
+    case = [c for c in _tab_cases() if c[0] == which][0]
+    _check_table_objective(warp_ctx_tab32 if kernel == "tab32" else warp_ctx_g16, warp_ctx_no_tab, case, "logistic_multiplicative")
+
+
 @pytest.mark.parametrize("which", ["day_table_15min", "week_table_hourly"])
 def test_table_variants_fit_and_forecast(warp_ctx, which):
     b, variant = {c[0]: (c[1], c[2]) for c in _tab_cases()}[which]
@@ -431,26 +457,3 @@ def test_table_variants_fit_and_forecast(warp_ctx, which):
     fb = batched.fit_batch_host(warp_ctx, batched.make_options(), b.ds, b.y, b.offsets, 0.0, 1.1)
     fb2 = batched.fit_batch_host(warp_ctx, batched.make_options(), b.ds, b.y, b.offsets, 0.0, 1.1)
     assert np.array_equal(fb.params, fb2.params) and np.array_equal(fb.meta_i32, fb2.meta_i32)   # deterministic
-
-
-# ---------------------------------------------------------------------------------------
-# EXPERIMENTAL phase-aligned engines (csrc/fit_inst_aligned.cu, PB200_ALIGN=1): not on the product path and not
-# yet run on hardware when this was written, so the test only runs on request:
-#   PB200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k aligned
-# ---------------------------------------------------------------------------------------
-@pytest.mark.skipif(os.environ.get("PB200_TEST_EXPERIMENTAL") != "1", reason="experimental kernel variant: opt-in")
-def test_aligned_engines_fit_is_bit_identical_to_the_product_kernel(warp_ctx):
-    b = synth.config3(n=200)                 # 200 series over 16-engine CTAs: some CTAs retire engines early
-    opts = batched.make_options()
-    ref = batched.fit_batch_host(warp_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
-    assert warp_ctx.last_fit_variant_counts()[3, 6] == b.n
-    actx = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_ALIGN=1)
-    try:
-        got = batched.fit_batch_host(actx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
-        assert actx.last_fit_variant_counts()[3, 6] == b.n
-    finally:
-        actx.close()
-    # the same per-series arithmetic in the same order: only the scheduling differs
-    assert np.array_equal(ref.params, got.params)
-    assert np.array_equal(ref.meta_i32, got.meta_i32)
-    assert np.array_equal(ref.meta_f64, got.meta_f64)

@@ -19,6 +19,8 @@ SEAS_AUTO = -1
 
 # per-series status codes (include/prophet_b200.h)
 ST_ABSX, ST_ABSF, ST_RELF, ST_ABSGRAD, ST_RELGRAD, ST_MAXIT, ST_CONST_LINEAR = 10, 20, 21, 30, 31, 40, 50
+ST_NEWTON = 60
+ALG_LBFGS_NEWTON, ALG_LBFGS, ALG_NEWTON = 0, 1, 2
 ST_LSFAIL, ST_INIT_ERROR, ST_TOO_FEW, ST_CAP_LE_FLOOR, ST_BAD_INPUT = -1, -2, -3, -4, -5
 
 
@@ -32,7 +34,7 @@ class Options(C.Structure):
         ("max_iter", C.c_int32), ("history_size", C.c_int32),
         ("init_alpha", C.c_double), ("tol_obj", C.c_double), ("tol_rel_obj", C.c_double),
         ("tol_grad", C.c_double), ("tol_rel_grad", C.c_double), ("tol_param", C.c_double),
-        ("interval_width", C.c_double), ("uncertainty_samples", C.c_int32), ("reserved", C.c_int32),
+        ("interval_width", C.c_double), ("uncertainty_samples", C.c_int32), ("algorithm", C.c_int32),
     ]
 
 
@@ -46,6 +48,7 @@ EXPORTS = [
     "pb200_default_options", "pb200_get_layout", "pb200_create", "pb200_destroy", "pb200_last_error",
     "pb200_stream", "pb200_launch_count", "pb200_last_fit_variant_counts", "pb200_tab_chunk", "pb200_fit_device", "pb200_fit_host", "pb200_predict_device",
     "pb200_predict_host", "pb200_make_future_device", "pb200_synchronize", "pb200_objective_host",
+    "pb200_fit_trace_host",
 ]
 
 _lib = None
@@ -95,6 +98,8 @@ def load() -> C.CDLL:
     lib.pb200_make_future_device.restype = C.c_int
     lib.pb200_objective_host.argtypes = [vp, OP, vp, vp, i32, vp, i64, dbl, dbl, vp, vp, vp, vp]
     lib.pb200_objective_host.restype = C.c_int
+    lib.pb200_fit_trace_host.argtypes = [vp, OP, vp, vp, i32, vp, i64, dbl, dbl, vp, vp, vp, vp, vp, vp, i32]
+    lib.pb200_fit_trace_host.restype = C.c_int
     lib.pb200_synchronize.argtypes = [vp]
     lib.pb200_synchronize.restype = C.c_int
     _lib = lib

@@ -22,7 +22,7 @@ def make_options(growth: str = "logistic", seasonality_mode: str = "multiplicati
                  n_changepoints: int = 25, changepoint_range: float = 0.8,
                  changepoint_prior_scale: float = 0.05, seasonality_prior_scale: float = 10.0,
                  interval_width: float = 0.8, uncertainty_samples: int = 1000,
-                 max_iter: int = 10000) -> L.Options:
+                 max_iter: int = 10000, algorithm: str = "LBFGS+Newton") -> L.Options:
     """Prophet.__init__ arguments -> pb200_options.  Defaults = the reference's hard-coded
     ``Prophet(growth='logistic', seasonality_mode='multiplicative')`` (prophet_modeler.py:65)."""
     o = L.default_options()
@@ -54,6 +54,7 @@ def make_options(growth: str = "logistic", seasonality_mode: str = "multiplicati
     o.interval_width = float(interval_width)
     o.uncertainty_samples = int(uncertainty_samples)
     o.max_iter = int(max_iter)
+    o.algorithm = {"LBFGS+Newton": L.ALG_LBFGS_NEWTON, "LBFGS": L.ALG_LBFGS, "Newton": L.ALG_NEWTON}[algorithm]
     return o
 
 
@@ -122,6 +123,30 @@ def fit_batch_host(ctx: L.Context, opts: L.Options, ds_ns: np.ndarray, y: np.nda
                                      _np_ptr(params), _np_ptr(tchange), _np_ptr(mi32), _np_ptr(mi64), _np_ptr(mf64))
         L.check(rc, "pb200_fit_host")
     return FittedBatch(params, tchange, mi32, mi64, mf64, lay.smax, lay.kmax)
+
+
+def fit_batch_trace_host(ctx: L.Context, opts: L.Options, ds_ns: np.ndarray, y: np.ndarray, offsets: np.ndarray,
+                         floor: float, cap_multiplier: float, trace_cap: int = 256):
+    """pb200_fit_trace_host (parity-test hook): the fit plus, per series, one row
+    ``(iteration, f_k, alpha_k, n_evals)`` per accepted L-BFGS iteration (``[n, trace_cap, 4]``)."""
+    ds_ns = np.ascontiguousarray(ds_ns, dtype=np.int64)
+    y = np.ascontiguousarray(y)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    lay = L.get_layout(opts)
+    params = np.empty((n, lay.pstride), np.float64)
+    tchange = np.empty((n, lay.smax), np.float64)
+    mi32 = np.empty((n, 8), np.int32)
+    mi64 = np.empty((n, 2), np.int64)
+    mf64 = np.empty((n, 4), np.float64)
+    trace = np.zeros((n, trace_cap, 4), np.float64)
+    if n > 0:
+        rc = L.load().pb200_fit_trace_host(ctx.handle, C.byref(opts), _np_ptr(ds_ns), _np_ptr(y), _y_dtype(y),
+                                           _np_ptr(offsets), n, float(floor), float(cap_multiplier),
+                                           _np_ptr(params), _np_ptr(tchange), _np_ptr(mi32), _np_ptr(mi64), _np_ptr(mf64),
+                                           _np_ptr(trace), int(trace_cap))
+        L.check(rc, "pb200_fit_trace_host")
+    return FittedBatch(params, tchange, mi32, mi64, mf64, lay.smax, lay.kmax), trace
 
 
 def fit_batch_device(ctx: L.Context, opts: L.Options, ds_ns, y, offsets_host: np.ndarray,

@@ -5,6 +5,7 @@
 #include "launch.h"
 #include "predict_kernel.cuh"
 #include "mc_kernel.cuh"
+#include "newton_kernel.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -98,8 +99,10 @@ struct pb200_ctx {
     DevBuf d_planes; // fit kernel planes workspace (one slice per resident CTA)
     int lc_max[NLC];
     bool lc_auto = true;   // false when PB200_LC*_MAX pins the CTA width
-    bool tab_on = true;    // PB200_NO_TAB=1 disables the seasonal-table variant (A/B runs)
-    bool align_on = false; // PB200_ALIGN=1: experimental phase-aligned 16-engine CTAs for the day-table class (fit_inst_aligned.cu)
+    bool tab_on = true;    // PB200_NO_TAB=1 disables the seasonal-table variants (A/B runs)
+    int grp_g = 8;         // lanes per series of the grouped day-table kernel (fit_group.cuh); PB200_GROUP=0|8|16, 0 = point_pass_tab
+    DevBuf d_nq;           // [0] count, [1..N] series whose L-BFGS failed its line search (Newton retry queue)
+    DevBuf d_trace;        // trajectory rows of pb200_fit_trace_host
 };
 
 namespace {
@@ -107,9 +110,6 @@ namespace {
 using pb200::FitArgs;
 using pb200::FitOptsDev;
 using pb200::NQ;
-
-extern "C" int pb200_launch_fit_aligned(int logi, const void* args, int grid, void* stream, int* occ);   // fit_inst_aligned.cu
-extern "C" int pb200_aligned_geometry(int* engines, int* slice_bytes, int* args_bytes);
 
 typedef cudaError_t (*launch_fn)(int, int, int, const FitArgs&, int, size_t, cudaStream_t, int*);
 const launch_fn LAUNCH[8] = {pb200::launch_fit_mask0, pb200::launch_fit_mask1, pb200::launch_fit_mask2,
@@ -127,6 +127,7 @@ int check_opts(const pb200_options* o) {
     for (int v : {o->yearly, o->weekly, o->daily})
         if (v != PB200_SEAS_AUTO && v != 0 && v != 1) return fail(PB200_E_UNSUPPORTED, "seasonality switch must be AUTO, 0 or 1");
     if (o->max_iter < 1) return fail(PB200_E_ARG, "max_iter");
+    if (o->algorithm < PB200_ALG_LBFGS_NEWTON || o->algorithm > PB200_ALG_NEWTON) return fail(PB200_E_ARG, "algorithm");
     return PB200_OK;
 }
 
@@ -247,7 +248,8 @@ PB200_API pb200_ctx* pb200_create(int device) {
     c->lc_max[2] = 1 << 30;
     c->lc_auto = !(getenv("PB200_LC0_MAX") || getenv("PB200_LC1_MAX"));
     c->tab_on = env_int("PB200_NO_TAB", 0) == 0;
-    c->align_on = env_int("PB200_ALIGN", 0) != 0;
+    c->grp_g = env_int("PB200_GROUP", 8);
+    if (c->grp_g != 8 && c->grp_g != 16) c->grp_g = 0;
     return c;
 }
 
@@ -257,7 +259,7 @@ PB200_API void pb200_destroy(pb200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_offsets, &c->d_order, &c->d_lenclass, &c->d_qitems, &c->d_qctl, &c->d_ds, &c->d_y, &c->d_cap,
                       &c->d_params, &c->d_tchange, &c->d_mi32, &c->d_mi64, &c->d_mf64, &c->d_fut, &c->d_floor, &c->d_yhat,
-                      &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc, &c->d_planes})
+                      &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc, &c->d_planes, &c->d_nq, &c->d_trace})
         b->release();
     c->h_ctl.release();
     cudaEventDestroy(c->ctl_ev);
@@ -299,7 +301,8 @@ PB200_API int pb200_synchronize(pb200_ctx* c) {
 static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds, const void* d_y, int32_t y_dtype,
                     const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
                     const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
-                    int64_t* d_meta_i64, double* d_meta_f64, const double* d_theta_in, double* d_grad_out) {
+                    int64_t* d_meta_i64, double* d_meta_f64, const double* d_theta_in, double* d_grad_out,
+                    double* d_trace = nullptr, int trace_cap = 0) {
     if (!c) return fail(PB200_E_ARG, "ctx is null");
     int rc = check_opts(opts);
     if (rc) return rc;
@@ -358,6 +361,8 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     CK(c->d_lenclass.reserve((size_t)N * 4));
     CK(c->d_qitems.reserve((size_t)NLC * NQ * N * 4));
     CK(c->d_qctl.reserve((size_t)NLC * NQ * 2 * 4));
+    CK(c->d_nq.reserve((size_t)(N + 2) * 4));                 // count, head, items[N]
+    CK(cudaMemsetAsync(c->d_nq.p, 0, 8, c->stream));
     CK(cudaMemcpyAsync(c->d_offsets.p, ho, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_order.p, horder, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_lenclass.p, hlc, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
@@ -392,6 +397,10 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         pa.tab_lc_mask = 0;
         for (int lc = 0; lc < NLC; ++lc)
             if (c->tab_on && LC_NT[lc] == 32) pa.tab_lc_mask |= 1 << lc;
+        pa.grp_g = c->tab_on ? c->grp_g : 0;
+        pa.newton_only = (opts->algorithm == PB200_ALG_NEWTON && !d_theta_in) ? 1 : 0;
+        pa.nq_count = (int*)c->d_nq.p;
+        pa.nq_items = (int*)c->d_nq.p + 2;
         const int warps_per_block = 8;
         int grid = (N + warps_per_block - 1) / warps_per_block;
         grid = std::min(grid, c->sms * 8);
@@ -401,9 +410,8 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
     }
     // ---- fit kernels: one persistent launch per (length class, seasonality class) ----
     // pass 1: launch geometry and the planes workspace (one slice per resident CTA)
-    struct Geo { int grid, Tp, ppad; size_t smem, slice, off; bool on, aligned; };
-    int al_engines = 0, al_slice = 0, al_args = 0;
-    pb200_aligned_geometry(&al_engines, &al_slice, &al_args);
+    struct Geo { int grid, Tp, ppad; size_t smem, slice, off; bool on, grouped; };
+    const int grp_g = c->tab_on ? c->grp_g : 0;
     Geo geo[NLC][NQ];       // [length class][variant * 8 + seasonality class]
     size_t planes_bytes = 0;
     for (int lc = 0; lc < NLC; ++lc)
@@ -411,7 +419,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             const int mask = rm & 7, reg = rm >> 3;
             Geo& g = geo[lc][rm];
             g.on = false;
-            g.aligned = false;
+            g.grouped = false;
             if (lc_n[lc] == 0) continue;
             if (reg && mask == 0) continue;       // no Fourier features: nothing to regenerate
             if (reg >= 2 && (mask != 6 || LC_NT[lc] != 32 || !c->tab_on)) continue;   // seasonal-table variants
@@ -430,13 +438,15 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             FitArgs dummy{};
             g.slice = (size_t)(1 + nst) * g.Tp;                   // double2 elements
             g.off = planes_bytes;
-            if (reg == 3 && c->align_on && g.smem <= (size_t)al_slice && al_args == (int)sizeof(FitArgs)) {
-                // experimental: CTAs of al_engines phase-aligned one-warp engines (one planes slice per engine)
-                if (pb200_launch_fit_aligned(opts->growth, &dummy, 0, c->stream, &occ) != 0 || occ < 1)
-                    return fail(PB200_E_UNSUPPORTED, "aligned fit kernel does not fit on an SM");
-                g.aligned = true;
-                g.grid = (int)std::min<int64_t>(((int64_t)lc_n[lc] + al_engines - 1) / al_engines, (int64_t)c->sms * occ);
-                planes_bytes += (size_t)g.grid * al_engines * g.slice * 16;
+            if (reg == 3 && grp_g > 0) {
+                // grouped day-table kernel: one warp per CTA, 32 / grp_g series per warp, one workspace slot per series
+                const int nser = 32 / grp_g;
+                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, dummy, 0, c->stream, &occ));
+                if (occ < 1) return fail(PB200_E_UNSUPPORTED, "grouped fit kernel does not fit on an SM");
+                g.grouped = true;
+                g.slice = pb200::fit_group_plane_doubles(lc_tmax[lc], grp_g);           // doubles per slot
+                g.grid = (int)std::min<int64_t>(((int64_t)lc_n[lc] + nser - 1) / nser, (int64_t)c->sms * occ);
+                planes_bytes += (size_t)g.grid * nser * g.slice * 8;
                 g.on = true;
                 continue;
             }
@@ -479,15 +489,44 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             fa.nseas_stride = (int)g.slice;
             fa.theta_in = d_theta_in;
             fa.grad_out = d_grad_out;
+            fa.trace = d_trace;
+            fa.trace_cap = trace_cap;
+            fa.nq_count = (int*)c->d_nq.p;
+            fa.nq_items = opts->algorithm == PB200_ALG_LBFGS_NEWTON ? (int*)c->d_nq.p + 2 : nullptr;
             fa.o = od;
-            if (g.aligned) {
-                if (pb200_launch_fit_aligned(opts->growth, &fa, g.grid, c->stream, nullptr) != 0)
-                    return fail(PB200_E_CUDA, "aligned fit kernel launch", cudaGetLastError());
+            if (g.grouped) {
+                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, fa, g.grid, c->stream, nullptr));
             } else {
                 CK(LAUNCH[mask](NT, opts->growth, reg, fa, g.grid, smem, c->stream, nullptr));
             }
             c->launches++;
         }
+    }
+    // ---- fbprophet's Newton retry over the series whose L-BFGS failed its line search (normally an empty queue) ----
+    if (opts->algorithm != PB200_ALG_LBFGS && !d_theta_in && L.pstride <= pb200::nw::NW_PMAX) {
+        pb200::nw::NewtonArgs na;
+        na.ds = (const long long*)d_ds;
+        na.y = d_y;
+        na.y_dtype = y_dtype;
+        na.offsets = (const long long*)c->d_offsets.p;
+        na.nq_count = (const int*)c->d_nq.p;
+        na.nq_head = (int*)c->d_nq.p + 1;
+        na.nq_items = (const int*)c->d_nq.p + 2;
+        na.params = d_params;
+        na.tchange = d_tchange;
+        na.meta_i32 = d_meta_i32;
+        na.meta_i64 = (const long long*)d_meta_i64;
+        na.meta_f64 = d_meta_f64;
+        na.smax = L.smax;
+        na.kmax = L.kmax;
+        na.pstride = L.pstride;
+        na.o = od;
+        const size_t nsm = pb200::nw::newton_smem_bytes(L.pstride);
+        CK(cudaFuncSetAttribute(pb200::nw::newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsm));
+        const int ngrid = (int)std::min<int64_t>(N, opts->algorithm == PB200_ALG_NEWTON ? (int64_t)c->sms * 2 : (int64_t)c->sms);
+        pb200::nw::newton_kernel<<<ngrid, 32 * pb200::nw::NW_WARPS, nsm, c->stream>>>(na);
+        CK(cudaGetLastError());
+        c->launches++;
     }
     return PB200_OK;
 }
@@ -582,6 +621,48 @@ PB200_API int pb200_fit_host(pb200_ctx* c, const pb200_options* opts, const int6
     CK(cudaMemcpyAsync(h_meta_i32, c->d_mi32.p, N * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_meta_i64, c->d_mi64.p, N * 2 * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_meta_f64, c->d_mf64.p, N * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PB200_OK;
+}
+
+PB200_API int pb200_fit_trace_host(pb200_ctx* c, const pb200_options* opts, const int64_t* h_ds, const void* h_y, int32_t y_dtype,
+                         const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier, double* h_params,
+                         double* h_tchange, int32_t* h_meta_i32, int64_t* h_meta_i64, double* h_meta_f64, double* h_trace,
+                         int32_t trace_cap) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (n_series <= 0) return n_series == 0 ? PB200_OK : fail(PB200_E_ARG, "n_series");
+    if (!h_ds || !h_y || !h_offsets || !h_params || !h_tchange || !h_meta_i32 || !h_meta_i64 || !h_meta_f64 || !h_trace)
+        return fail(PB200_E_ARG, "null pointer");
+    if (y_dtype < 0 || y_dtype > 2) return fail(PB200_E_ARG, "y_dtype");
+    if (trace_cap < 1 || (int64_t)trace_cap * n_series > (1LL << 26)) return fail(PB200_E_ARG, "trace_cap");
+    pb200_layout L;
+    pb200_get_layout(opts, &L);
+    CK(cudaSetDevice(c->device));
+    const int64_t R = h_offsets[n_series];
+    const size_t N = (size_t)n_series, tbytes = N * (size_t)trace_cap * 4 * 8;
+    CK(c->d_ds.reserve((size_t)R * 8));
+    CK(c->d_y.reserve((size_t)R * y_elem(y_dtype)));
+    CK(c->d_params.reserve(N * L.pstride * 8));
+    CK(c->d_tchange.reserve(N * L.smax * 8));
+    CK(c->d_mi32.reserve(N * 8 * 4));
+    CK(c->d_mi64.reserve(N * 2 * 8));
+    CK(c->d_mf64.reserve(N * 4 * 8));
+    CK(c->d_trace.reserve(tbytes));
+    CK(cudaMemcpyAsync(c->d_ds.p, h_ds, (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_y.p, h_y, (size_t)R * y_elem(y_dtype), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_trace.p, 0, tbytes, c->stream));
+    rc = fit_impl(c, opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype, h_offsets, n_series, floor, cap_multiplier, nullptr,
+                  (double*)c->d_params.p, (double*)c->d_tchange.p, (int32_t*)c->d_mi32.p, (int64_t*)c->d_mi64.p,
+                  (double*)c->d_mf64.p, nullptr, nullptr, (double*)c->d_trace.p, trace_cap);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_params, c->d_params.p, N * L.pstride * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_tchange, c->d_tchange.p, N * L.smax * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_meta_i32, c->d_mi32.p, N * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_meta_i64, c->d_mi64.p, N * 2 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_meta_f64, c->d_mf64.p, N * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_trace, c->d_trace.p, tbytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return PB200_OK;
 }

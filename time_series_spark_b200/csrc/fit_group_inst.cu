@@ -1,0 +1,36 @@
+// Instantiations of the grouped-lanes fit kernel (fit_group.cuh): G in {8, 16} lanes per series x growth x
+// seasonality mode, for the weekly + daily day-table class.
+#include "fit_group.cuh"
+#include "launch.h"
+
+namespace pb200 {
+
+template <int G, bool LOGI, bool MULT>
+static cudaError_t launch_group_one(const FitArgs& a, int grid, cudaStream_t st, int* occ) {
+    auto kern = grp::fit_group_kernel<G, LOGI, MULT>;
+    const size_t smem = grp::group_smem_bytes<G>();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, 32, smem);
+    kern<<<grid, 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int G>
+static cudaError_t launch_group_g(int logi, int mult, const FitArgs& a, int grid, cudaStream_t st, int* occ) {
+    if (logi) return mult ? launch_group_one<G, true, true>(a, grid, st, occ) : launch_group_one<G, true, false>(a, grid, st, occ);
+    return mult ? launch_group_one<G, false, true>(a, grid, st, occ) : launch_group_one<G, false, false>(a, grid, st, occ);
+}
+
+cudaError_t launch_fit_group(int g, int logi, int mult, const FitArgs& a, int grid, cudaStream_t st, int* occ) {
+    if (g == 8) return launch_group_g<8>(logi, mult, a, grid, st, occ);
+    if (g == 16) return launch_group_g<16>(logi, mult, a, grid, st, occ);
+    return cudaErrorInvalidValue;
+}
+
+size_t fit_group_plane_doubles(int tmax, int g) {
+    size_t d = grp::group_plane_doubles(tmax, g) + grp::GHIST;
+    return (d + 1) & ~(size_t)1;
+}
+
+}  // namespace pb200

@@ -95,7 +95,9 @@ class _ModelTimeSeriesOp:
         torch.cuda.set_device(ctx.device)
         pk = pack_groups_cuda(table, device=f"cuda:{ctx.device}")
         rank, ws, _ = pdist.world()
-        if ws > 1:      # one process per GPU: this rank fits its contiguous, row-balanced shard of the groups
+        if ws > 1 and not getattr(self, "rank_local_input", False):
+            # the table holds EVERY group (the caller did not read rank-locally): this rank fits its contiguous,
+            # row-balanced shard of them
             lo, hi = pdist.shard_bounds(pk.offsets, ws)[rank]
             pk = pk.take(lo, hi)
         if pk.n == 0:
@@ -104,15 +106,21 @@ class _ModelTimeSeriesOp:
         print(f"Modeling {pk.n} series with {int(pk.offsets[-1])} modeling rows")
         # fbprophet raises ValueError (task failure, not RuntimeError) for < 2 rows:
         # keep that observable behaviour (prophet_modeler.py:81 only catches RuntimeError)
-        if np.any(np.diff(pk.offsets) < 2):
-            raise ValueError("Dataframe has less than 2 non-NaN rows.")
+        def _who(mask):
+            i = int(np.flatnonzero(mask)[0])
+            return (f" (first offender: series_id {int(pk.series_id[i])}, dim_id {int(pk.dim_id[i])}; "
+                    f"{int(np.count_nonzero(mask))} group(s) in all)")
+
+        short = np.diff(pk.offsets) < 2
+        if np.any(short):
+            raise ValueError("Dataframe has less than 2 non-NaN rows." + _who(short))
         fitted = batched.fit_batch_device(ctx, opts, pk.ds.contiguous(), pk.y.contiguous(), pk.offsets,
                                           float(floor), float(cap_multiplier)).to_host()
         status = fitted.meta_i32[:, 4]
         if np.any(status == L.ST_CAP_LE_FLOOR):
-            raise ValueError("cap must be greater than floor (which defaults to 0).")
+            raise ValueError("cap must be greater than floor (which defaults to 0)." + _who(status == L.ST_CAP_LE_FLOOR))
         if np.any(status == L.ST_BAD_INPUT):
-            raise ValueError("Found non-finite y or a zero time span in a series.")
+            raise ValueError("Found non-finite y or a zero time span in a series." + _who(status == L.ST_BAD_INPUT))
         ok = status >= 0
         for i in np.flatnonzero(~ok):
             # reference: RuntimeError -> print + empty frame (prophet_modeler.py:81-85)
@@ -137,6 +145,31 @@ class _ModelTimeSeriesOp:
         still iterate groups themselves."""
         tbl = pa.Table.from_pandas(pdf[["series_id", "dim_id", "ds", "y"]], preserve_index=False)
         return self.apply_batched(tbl, ["series_id", "dim_id"]).to_pandas()
+
+
+def rank_local_files(dset, rank: int, world_size: int):
+    """Files of the hive-partitioned input this rank reads: the ``series_id=`` directories in ascending id order,
+    cut into ``world_size`` contiguous ranges of (nearly) equal bytes.  Returns None when there are fewer
+    directories than ranks (the caller then reads everything and shards the packed groups instead)."""
+    by_sid = {}
+    for f in dset.get_fragments():
+        sid = pads.get_partition_keys(f.partition_expression).get("series_id")
+        if sid is None:
+            return None
+        try:
+            size = os.path.getsize(f.path)
+        except OSError:
+            size = 1
+        ent = by_sid.setdefault(int(sid), [0, []])
+        ent[0] += max(size, 1)
+        ent[1].append(f.path)
+    sids = sorted(by_sid)
+    if len(sids) < world_size:
+        return None
+    sizes = np.array([by_sid[s][0] for s in sids], dtype=np.int64)
+    offs = np.concatenate(([0], np.cumsum(sizes)))
+    lo, hi = pdist.shard_bounds(offs, world_size)[rank]
+    return [p for s in sids[lo:hi] for p in sorted(by_sid[s][1])]
 
 
 def model_time_series(config):
@@ -165,6 +198,22 @@ class ProphetModeler:
                 timestamp_parsers=["%Y-%m-%d %H:%M:%S", pacsv.ISO8601]))
         dset = pads.dataset(path, format=fmt, partitioning=part, exclude_invalid_files=False,
                             ignore_prefixes=[".", "_"])
+        # Rank-local ingestion: a group never spans two ``series_id=`` directories, so under torchrun each
+        # rank parses, uploads and sorts only its own contiguous, byte-balanced range of directories -- the
+        # counterpart of Spark tasks reading their own input splits.  With fewer directories than ranks every
+        # rank reads everything and the groups are range-sharded after the pack instead.
+        rank, ws, _ = pdist.world()
+        self.rank_local_input = False
+        if ws > 1:
+            mine = rank_local_files(dset, rank, ws)
+            if mine is not None:
+                self.rank_local_input = True
+                if not mine:
+                    empty = pa.schema([("series_id", pa.int32()), ("dim_id", pa.int32()), ("ds", pa.timestamp("ns")),
+                                       ("y", pa.int32())]).empty_table()
+                    return Frame(empty)
+                dset = pads.dataset(mine, format=fmt, partitioning=part, partition_base_dir=path,
+                                    exclude_invalid_files=False)
         tbl = dset.to_table(columns=["series_id", "dim_id", "start_time", "quantity"])
         tbl = tbl.rename_columns(["series_id", "dim_id", "ds", "y"])
         return Frame(tbl)
@@ -182,5 +231,7 @@ class ProphetModeler:
         pdist.init_process_group()          # no-op unless launched by torchrun with WORLD_SIZE > 1
         scorer = ProphetModeler(config)
         input_df = scorer.read_input_dataframe(spark_session)
-        model_df = input_df.groupby("series_id", "dim_id").apply(model_time_series(scorer.config))
+        op = model_time_series(scorer.config)
+        op.rank_local_input = getattr(scorer, "rank_local_input", False)
+        model_df = input_df.groupby("series_id", "dim_id").apply(op)
         scorer.persist_models(model_df)

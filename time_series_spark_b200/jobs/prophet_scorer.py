@@ -104,8 +104,13 @@ class _ForecastTimeSeriesOp:
         if ws > 1 and table.num_rows:      # shard the model rows across ranks (equal horizon => equal work)
             lo, hi = pdist.shard_bounds(np.arange(table.num_rows + 1, dtype=np.int64), ws)[rank]
             table = table.slice(lo, hi - lo)
+        # every rank must hand back the same columns (an empty shard too): the optional gather issues one
+        # collective per column
+        empty_schema = FORECAST_SCHEMA
+        if want_intervals:
+            empty_schema = empty_schema.append(pa.field("yhat_lower", pa.float64())).append(pa.field("yhat_upper", pa.float64()))
         if table.num_rows == 0:
-            return FORECAST_SCHEMA.empty_table()
+            return empty_schema.empty_table()
         # model is None -> "no model found", empty frame for that group (reference :51-55)
         mcol = table["model"]
         if mcol.null_count:
@@ -114,7 +119,7 @@ class _ForecastTimeSeriesOp:
                 print(f"For series_id: {sid}, dim_id: {did}, no model found")
             table = table.filter(pc.is_valid(mcol))
             if table.num_rows == 0:
-                return FORECAST_SCHEMA.empty_table()
+                return empty_schema.empty_table()
         fitted, last_ds, info = model_record.decode(table["model"])
         opts = batched.make_options(growth="logistic" if info["logistic"] else "linear",
                                     seasonality_mode="multiplicative" if info["multiplicative"] else "additive",
@@ -205,9 +210,12 @@ class ProphetScorer:
         pdist.prepare_output_dir(out)
         t = output_df.table
         if "forecast_timestamp" in t.column_names and pa.types.is_timestamp(t["forecast_timestamp"].type):
-            # Spark's CSV writer prints timestamps as yyyy-MM-dd'T'HH:mm:ss.SSSXXX by default
+            # Spark's CSV writer prints timestamps as yyyy-MM-dd'T'HH:mm:ss.SSSXXX by default, e.g.
+            # 2019-01-01T00:00:05.000Z.  Arrow's %S prints the fraction at the column's unit, so the column is
+            # cast to milliseconds first (a timestamp[ns] column would print nine digits).
             i = t.column_names.index("forecast_timestamp")
-            t = t.set_column(i, "forecast_timestamp", pc.strftime(t["forecast_timestamp"], format="%Y-%m-%dT%H:%M:%S.000Z"))
+            ms = pc.cast(t["forecast_timestamp"], pa.timestamp("ms"), safe=False)
+            t = t.set_column(i, "forecast_timestamp", pc.strftime(ms, format="%Y-%m-%dT%H:%M:%SZ"))
         pacsv.write_csv(t, os.path.join(out, f"part-{rank:05d}.csv"),
                         write_options=pacsv.WriteOptions(include_header=True, quoting_style="needed"))
 

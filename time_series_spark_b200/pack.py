@@ -48,12 +48,24 @@ def _pinned_like(a: np.ndarray) -> np.ndarray:
             t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
             out = t.numpy()
             out[...] = a
-            out_base = out
-            out_base._pin_owner = t if hasattr(out_base, "__dict__") else None  # keep alive below
             return _Keep(out, t)
     except Exception:
         pass
     return a
+
+
+def _group_keys(table: pa.Table, keys):
+    """The two int group-key columns as int64 numpy arrays.  A null key is refused: Spark would make null its own
+    group, and the reference's fixed schema never produces one (series_id comes from the directory name, an empty
+    dim_id field is a malformed row) -- silently merging it into another group would be worse than failing."""
+    out = []
+    for k in keys[:2]:
+        col = table[k]
+        if col.null_count:
+            raise ValueError(f"group key column {k!r} holds {col.null_count} null value(s); every row needs both "
+                             f"{keys[0]!r} and {keys[1]!r}")
+        out.append(np.asarray(col.combine_chunks().to_numpy(zero_copy_only=False)).astype(np.int64))
+    return out
 
 
 class _Keep(np.ndarray):
@@ -81,8 +93,7 @@ def pack_groups(table: pa.Table, keys=("series_id", "dim_id"), ds_col="ds", y_co
     else:
         ds_np = ds_arr.to_numpy() if isinstance(ds_arr, pa.Array) else ds_arr.combine_chunks().to_numpy()
         ds_np = np.asarray(ds_np, dtype=np.int64)
-    k0 = np.asarray(table[keys[0]].combine_chunks().to_numpy(zero_copy_only=False)).astype(np.int64)
-    k1 = np.asarray(table[keys[1]].combine_chunks().to_numpy(zero_copy_only=False)).astype(np.int64)
+    k0, k1 = _group_keys(table, keys)
     ycol = table[y_col].combine_chunks()
     y_null = np.asarray(ycol.is_null().to_numpy(zero_copy_only=False)) if ycol.null_count else None
     if pa.types.is_integer(ycol.type):
@@ -135,8 +146,7 @@ def pack_groups_cuda(table: pa.Table, device=None, keys=("series_id", "dim_id"),
             raise ValueError("Found NaN in column ds.")
         ds_arr = pc.cast(pc.cast(ds_arr, pa.timestamp("ns")), pa.int64())
     ds_np = np.asarray(ds_arr.combine_chunks().to_numpy(zero_copy_only=False), dtype=np.int64)
-    k0 = np.asarray(table[keys[0]].combine_chunks().to_numpy(zero_copy_only=False)).astype(np.int64)
-    k1 = np.asarray(table[keys[1]].combine_chunks().to_numpy(zero_copy_only=False)).astype(np.int64)
+    k0, k1 = _group_keys(table, keys)
     ycol = table[y_col].combine_chunks()
     integral = pa.types.is_integer(ycol.type)
     if integral:
@@ -145,9 +155,11 @@ def pack_groups_cuda(table: pa.Table, device=None, keys=("series_id", "dim_id"),
     else:
         y_np = np.asarray(ycol.to_numpy(zero_copy_only=False)).astype(np.float64)
         y_null = np.isnan(y_np) if np.isnan(y_np).any() else None
-    key = torch.from_numpy((k0 << 32) | (k1 & 0xFFFFFFFF)).to(dev)
-    ds_t = torch.from_numpy(ds_np).to(dev)
-    y_t = torch.from_numpy(y_np).to(dev)
+    # one signed 64-bit sort key: series_id in the high word, dim_id biased by 2^31 in the low word, so that the
+    # signed order of the key is the (series_id, dim_id) order of the host path's lexsort for negative ids too
+    key = torch.from_numpy(((k0 << 32) | ((k1 + (1 << 31)) & 0xFFFFFFFF)).copy()).to(dev)
+    ds_t = torch.from_numpy(np.array(ds_np, copy=True)).to(dev)      # (Arrow buffers are read-only: copy before wrapping)
+    y_t = torch.from_numpy(np.array(y_np, copy=True)).to(dev)
     i1 = torch.argsort(ds_t, stable=True)
     i2 = torch.argsort(key[i1], stable=True)
     order = i1[i2]
@@ -159,7 +171,7 @@ def pack_groups_cuda(table: pa.Table, device=None, keys=("series_id", "dim_id"),
     last_ds = ds_t[ends - 1].cpu().numpy()
     n_rows_in = (ends - starts).cpu().numpy().astype(np.int64)
     gkeys = key[starts].cpu().numpy()
-    sid, did = (gkeys >> 32).astype(np.int32), (gkeys & 0xFFFFFFFF).astype(np.int64).astype(np.int32)
+    sid, did = (gkeys >> 32).astype(np.int32), ((gkeys & 0xFFFFFFFF) - (1 << 31)).astype(np.int32)
     if y_null is not None and y_null.any():
         keep = ~torch.from_numpy(y_null).to(dev)[order]
         grp_id = torch.cumsum(new_grp.to(torch.int64), 0) - 1

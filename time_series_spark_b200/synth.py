@@ -112,6 +112,12 @@ def config2(n: int = 1000, T: int = 365, seed: int = 1234, lo: int = 0, hi: int 
                        (np.arange(m + 1, dtype=np.int64) * T), np.tile(grid, m), y.reshape(-1))
 
 
+# Config-#4 series (default seed) on which Stan's L-BFGS ends in a line-search failure under the default tolerances
+# (found with the C oracle over the whole 500k batch -- and none in 1.6 M series of four other seeds): the case
+# fbprophet 0.5 answers with its Newton retry.  Used by tests/test_gpu_optimiser.py.
+CONFIG4_LSFAIL_IDS = (148912,)
+
+
 def config4(n: int = 500_000, seed: int = 4321, lo: int = 0, hi: int | None = None,
             tmin: int = 48, tmax: int = 96) -> RaggedBatch:
     """Config #4: N short ragged series, T_i ~ U{48..96}, 15-min spacing (span < 2 days so
