@@ -381,7 +381,7 @@ def _tab_cases():
         ("week_table_hourly_T337", _regrid(c3, H, 337), 2),  # two weeks + 1 point: the shortest series with weekly
         ("week_table_2h", _regrid(c3, 2 * H), 2),            # P = 84, 120 days
         ("day_table_30min", _regrid(c3, 30 * 60 * 10**9), 3),    # P = 48: the smallest table of the grouped kernel
-        ("rotation_10min", _regrid(c3, 10 * 60 * 10**9), 1),     # P = 144 > 96 phases per day: no table
+        ("rotation_12min", _regrid(synth.config3(n=16, T=1800), 12 * 60 * 10**9), 1),   # P = 120 > 96 phases per day: no table
         ("rotation_25min", _regrid(c3, 25 * 60 * 10**9), 1),   # step divides neither day nor week: no table
     ]
 

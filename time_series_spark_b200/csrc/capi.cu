@@ -82,27 +82,37 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-struct pb200_ctx {
-    int device = 0;
-    int sms = 0;
+// Everything one in-flight fit call needs besides its inputs and outputs.  Two of them: the *_host entry point cuts
+// a big batch into series chunks and alternates them over the two (stream, workspace) pairs, so that the H2D copy of
+// chunk i + 1 overlaps the fit of chunk i and chunk i + 1's kernels fill the SMs chunk i's stragglers leave idle.
+struct FitWs {
     cudaStream_t stream = nullptr;
     cudaEvent_t ctl_ev = nullptr;   // recorded after the H2D copies out of h_ctl
     bool ctl_pending = false;
+    DevBuf d_offsets, d_order, d_lenclass, d_qitems, d_qctl;   // control workspace (device)
+    DevBuf d_nq;                    // [0] count, [1] head, [2..] series whose L-BFGS failed its line search (Newton retry queue)
+    DevBuf d_planes;                // fit kernels' per-series workspace (one slice per resident CTA / series slot)
+    HostBuf h_ctl;                  // pinned staging for offsets / order / lenclass
+};
+
+struct pb200_ctx {
+    int device = 0;
+    int sms = 0;
+    FitWs ws[2];
+    cudaStream_t stream = nullptr;  // = ws[0].stream: the stream of every single-workspace call
+    cudaEvent_t fork_ev = nullptr;
     int64_t launches = 0;
-    // control workspace (device)
-    DevBuf d_offsets, d_order, d_lenclass, d_qitems, d_qctl;
-    HostBuf h_ctl;   // pinned staging for offsets / order / lenclass
+    DevBuf d_vcount;                // series of the last fit call per kernel variant x seasonality class
     // data staging for the *_host entry points
     DevBuf d_ds, d_y, d_cap, d_params, d_tchange, d_mi32, d_mi64, d_mf64;
     DevBuf d_fut, d_floor, d_yhat, d_lo, d_hi, d_yint;
     DevBuf d_mc;     // MC workspace
-    DevBuf d_planes; // fit kernel planes workspace (one slice per resident CTA)
     int lc_max[NLC];
     bool lc_auto = true;   // false when PB200_LC*_MAX pins the CTA width
     bool tab_on = true;    // PB200_NO_TAB=1 disables the seasonal-table variants (A/B runs)
     int grp_g = 8;         // lanes per series of the grouped day-table kernel (fit_group.cuh); PB200_GROUP=0|8|16, 0 = point_pass_tab
-    DevBuf d_nq;           // [0] count, [1..N] series whose L-BFGS failed its line search (Newton retry queue)
     DevBuf d_trace;        // trajectory rows of pb200_fit_trace_host
+    int host_chunks = 4;   // PB200_HOST_CHUNKS: series chunks of pb200_fit_host (1 = no overlap)
 };
 
 namespace {
@@ -232,38 +242,47 @@ PB200_API pb200_ctx* pb200_create(int device) {
         delete c;
         return nullptr;
     }
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        fail(PB200_E_CUDA, "cudaStreamCreate");
+    bool ok = cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (FitWs& w : c->ws) {
+        ok = ok && cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&w.ctl_ev, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) {
+        fail(PB200_E_CUDA, "cudaStreamCreate / cudaEventCreate");
+        for (FitWs& w : c->ws) {
+            if (w.ctl_ev) cudaEventDestroy(w.ctl_ev);
+            if (w.stream) cudaStreamDestroy(w.stream);
+        }
+        if (c->fork_ev) cudaEventDestroy(c->fork_ev);
         delete c;
         return nullptr;
     }
-    if (cudaEventCreateWithFlags(&c->ctl_ev, cudaEventDisableTiming) != cudaSuccess) {
-        fail(PB200_E_CUDA, "cudaEventCreate");
-        cudaStreamDestroy(c->stream);
-        delete c;
-        return nullptr;
-    }
+    c->stream = c->ws[0].stream;
+    c->host_chunks = std::max(1, std::min(16, env_int("PB200_HOST_CHUNKS", 4)));
     c->lc_max[0] = env_int("PB200_LC0_MAX", 1 << 30);   // warp-per-series for every length
     c->lc_max[1] = env_int("PB200_LC1_MAX", 1 << 30);
     c->lc_max[2] = 1 << 30;
     c->lc_auto = !(getenv("PB200_LC0_MAX") || getenv("PB200_LC1_MAX"));
     c->tab_on = env_int("PB200_NO_TAB", 0) == 0;
     c->grp_g = env_int("PB200_GROUP", 8);
-    if (c->grp_g != 8 && c->grp_g != 16) c->grp_g = 0;
+    if (c->grp_g != 8 && c->grp_g != 16 && c->grp_g != 32) c->grp_g = 0;
     return c;
 }
 
 PB200_API void pb200_destroy(pb200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->d_offsets, &c->d_order, &c->d_lenclass, &c->d_qitems, &c->d_qctl, &c->d_ds, &c->d_y, &c->d_cap,
-                      &c->d_params, &c->d_tchange, &c->d_mi32, &c->d_mi64, &c->d_mf64, &c->d_fut, &c->d_floor, &c->d_yhat,
-                      &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc, &c->d_planes, &c->d_nq, &c->d_trace})
+    for (FitWs& w : c->ws) cudaStreamSynchronize(w.stream);
+    for (DevBuf* b : {&c->d_ds, &c->d_y, &c->d_cap, &c->d_params, &c->d_tchange, &c->d_mi32, &c->d_mi64, &c->d_mf64, &c->d_fut,
+                      &c->d_floor, &c->d_yhat, &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc, &c->d_trace, &c->d_vcount})
         b->release();
-    c->h_ctl.release();
-    cudaEventDestroy(c->ctl_ev);
-    cudaStreamDestroy(c->stream);
+    for (FitWs& w : c->ws) {
+        for (DevBuf* b : {&w.d_offsets, &w.d_order, &w.d_lenclass, &w.d_qitems, &w.d_qctl, &w.d_nq, &w.d_planes}) b->release();
+        w.h_ctl.release();
+        cudaEventDestroy(w.ctl_ev);
+        cudaStreamDestroy(w.stream);
+    }
+    cudaEventDestroy(c->fork_ev);
     delete c;
 }
 
@@ -279,26 +298,32 @@ PB200_API int pb200_last_fit_variant_counts(pb200_ctx* c, int32_t* h_counts) {
     if (!c || !h_counts) return fail(PB200_E_ARG, "null argument");
     static_assert(PB200_N_VARIANT_COUNTS == NQ, "variant count layout");
     for (int i = 0; i < NQ; ++i) h_counts[i] = 0;
-    if (!c->d_qctl.p) return PB200_OK;        // no fit yet
+    if (!c->d_vcount.p) return PB200_OK;      // no fit yet
     CK(cudaSetDevice(c->device));
-    int32_t tmp[NLC * NQ];
-    CK(cudaMemcpyAsync(tmp, c->d_qctl.p, sizeof(tmp), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    for (int lc = 0; lc < NLC; ++lc)
-        for (int i = 0; i < NQ; ++i) h_counts[i] += tmp[lc * NQ + i];
+    for (FitWs& w : c->ws) CK(cudaStreamSynchronize(w.stream));
+    CK(cudaMemcpy(h_counts, c->d_vcount.p, NQ * 4, cudaMemcpyDeviceToHost));
     return PB200_OK;
 }
 
 PB200_API int pb200_synchronize(pb200_ctx* c) {
     if (!c) return fail(PB200_E_ARG, "ctx is null");
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
+    for (FitWs& w : c->ws) CK(cudaStreamSynchronize(w.stream));
     return PB200_OK;
 }
 
 }  // extern "C"
 
-static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds, const void* d_y, int32_t y_dtype,
+// zero the per-call variant counters (on workspace 0's stream; workspace 1 is ordered behind it)
+static int begin_fit_call(pb200_ctx* c) {
+    CK(c->d_vcount.reserve(NQ * 4));
+    CK(cudaMemsetAsync(c->d_vcount.p, 0, NQ * 4, c->ws[0].stream));
+    CK(cudaEventRecord(c->fork_ev, c->ws[0].stream));
+    CK(cudaStreamWaitEvent(c->ws[1].stream, c->fork_ev, 0));
+    return PB200_OK;
+}
+
+static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int64_t* d_ds, const void* d_y, int32_t y_dtype,
                     const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
                     const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
                     int64_t* d_meta_i64, double* d_meta_f64, const double* d_theta_in, double* d_grad_out,
@@ -318,12 +343,12 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
 
     // ---- host: length classes and longest-first order (counting sort on T) ----
     size_t ctl_bytes = (size_t)(N + 1) * 8 + (size_t)N * 4 * 2;
-    if (c->ctl_pending) {   // the pinned staging of the previous call must have been consumed
-        CK(cudaEventSynchronize(c->ctl_ev));
-        c->ctl_pending = false;
+    if (w.ctl_pending) {   // the pinned staging of the previous call must have been consumed
+        CK(cudaEventSynchronize(w.ctl_ev));
+        w.ctl_pending = false;
     }
-    CK(c->h_ctl.reserve(ctl_bytes));
-    int64_t* ho = (int64_t*)c->h_ctl.p;
+    CK(w.h_ctl.reserve(ctl_bytes));
+    int64_t* ho = (int64_t*)w.h_ctl.p;
     int* horder = (int*)(ho + N + 1);
     int* hlc = horder + N;
     memcpy(ho, h_offsets, (size_t)(N + 1) * 8);
@@ -356,22 +381,22 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         }
     }
     // ---- device control buffers ----
-    CK(c->d_offsets.reserve((size_t)(N + 1) * 8));
-    CK(c->d_order.reserve((size_t)N * 4));
-    CK(c->d_lenclass.reserve((size_t)N * 4));
-    CK(c->d_qitems.reserve((size_t)NLC * NQ * N * 4));
-    CK(c->d_qctl.reserve((size_t)NLC * NQ * 2 * 4));
-    CK(c->d_nq.reserve((size_t)(N + 2) * 4));                 // count, head, items[N]
-    CK(cudaMemsetAsync(c->d_nq.p, 0, 8, c->stream));
-    CK(cudaMemcpyAsync(c->d_offsets.p, ho, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_order.p, horder, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_lenclass.p, hlc, (size_t)N * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaEventRecord(c->ctl_ev, c->stream));
-    c->ctl_pending = true;
-    CK(cudaMemsetAsync(c->d_qctl.p, 0, (size_t)NLC * NQ * 2 * 4, c->stream));
-    CK(cudaMemsetAsync(d_params, 0, (size_t)N * L.pstride * 8, c->stream));
-    CK(cudaMemsetAsync(d_tchange, 0, (size_t)N * L.smax * 8, c->stream));
-    int* q_count = (int*)c->d_qctl.p;
+    CK(w.d_offsets.reserve((size_t)(N + 1) * 8));
+    CK(w.d_order.reserve((size_t)N * 4));
+    CK(w.d_lenclass.reserve((size_t)N * 4));
+    CK(w.d_qitems.reserve((size_t)NLC * NQ * N * 4));
+    CK(w.d_qctl.reserve((size_t)NLC * NQ * 2 * 4));
+    CK(w.d_nq.reserve((size_t)(N + 2) * 4));                 // count, head, items[N]
+    CK(cudaMemsetAsync(w.d_nq.p, 0, 8, w.stream));
+    CK(cudaMemcpyAsync(w.d_offsets.p, ho, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, w.stream));
+    CK(cudaMemcpyAsync(w.d_order.p, horder, (size_t)N * 4, cudaMemcpyHostToDevice, w.stream));
+    CK(cudaMemcpyAsync(w.d_lenclass.p, hlc, (size_t)N * 4, cudaMemcpyHostToDevice, w.stream));
+    CK(cudaEventRecord(w.ctl_ev, w.stream));
+    w.ctl_pending = true;
+    CK(cudaMemsetAsync(w.d_qctl.p, 0, (size_t)NLC * NQ * 2 * 4, w.stream));
+    CK(cudaMemsetAsync(d_params, 0, (size_t)N * L.pstride * 8, w.stream));
+    CK(cudaMemsetAsync(d_tchange, 0, (size_t)N * L.smax * 8, w.stream));
+    int* q_count = (int*)w.d_qctl.p;
     int* q_head = q_count + NLC * NQ;
 
     const FitOptsDev od = to_dev(opts);
@@ -381,8 +406,8 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         pa.ds = (const long long*)d_ds;
         pa.y = d_y;
         pa.y_dtype = y_dtype;
-        pa.offsets = (const long long*)c->d_offsets.p;
-        pa.order = (const int*)c->d_order.p;
+        pa.offsets = (const long long*)w.d_offsets.p;
+        pa.order = (const int*)w.d_order.p;
         pa.cap = d_cap;
         pa.floor = floor;
         pa.cap_multiplier = cap_multiplier;
@@ -390,8 +415,8 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         pa.meta_i32 = d_meta_i32;
         pa.meta_i64 = (long long*)d_meta_i64;
         pa.meta_f64 = d_meta_f64;
-        pa.lenclass = (const int*)c->d_lenclass.p;
-        pa.q_items = (int*)c->d_qitems.p;
+        pa.lenclass = (const int*)w.d_lenclass.p;
+        pa.q_items = (int*)w.d_qitems.p;
         pa.q_count = q_count;
         pa.o = od;
         pa.tab_lc_mask = 0;
@@ -399,12 +424,13 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             if (c->tab_on && LC_NT[lc] == 32) pa.tab_lc_mask |= 1 << lc;
         pa.grp_g = c->tab_on ? c->grp_g : 0;
         pa.newton_only = (opts->algorithm == PB200_ALG_NEWTON && !d_theta_in) ? 1 : 0;
-        pa.nq_count = (int*)c->d_nq.p;
-        pa.nq_items = (int*)c->d_nq.p + 2;
+        pa.nq_count = (int*)w.d_nq.p;
+        pa.nq_items = (int*)w.d_nq.p + 2;
+        pa.vcount = (int*)c->d_vcount.p;
         const int warps_per_block = 8;
         int grid = (N + warps_per_block - 1) / warps_per_block;
         grid = std::min(grid, c->sms * 8);
-        pb200::prep_kernel<<<grid, warps_per_block * 32, 0, c->stream>>>(pa);
+        pb200::prep_kernel<<<grid, warps_per_block * 32, 0, w.stream>>>(pa);
         CK(cudaGetLastError());
         c->launches++;
     }
@@ -441,7 +467,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             if (reg == 3 && grp_g > 0) {
                 // grouped day-table kernel: one warp per CTA, 32 / grp_g series per warp, one workspace slot per series
                 const int nser = 32 / grp_g;
-                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, dummy, 0, c->stream, &occ));
+                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, dummy, 0, w.stream, &occ));
                 if (occ < 1) return fail(PB200_E_UNSUPPORTED, "grouped fit kernel does not fit on an SM");
                 g.grouped = true;
                 g.slice = pb200::fit_group_plane_doubles(lc_tmax[lc], grp_g);           // doubles per slot
@@ -450,13 +476,13 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
                 g.on = true;
                 continue;
             }
-            CK(LAUNCH[mask](NT, opts->growth, reg, dummy, 0, g.smem, c->stream, &occ));
+            CK(LAUNCH[mask](NT, opts->growth, reg, dummy, 0, g.smem, w.stream, &occ));
             if (occ < 1) return fail(PB200_E_UNSUPPORTED, "fit kernel does not fit on an SM");
             g.grid = (int)std::min<int64_t>((int64_t)lc_n[lc], (int64_t)c->sms * occ);
             planes_bytes += (size_t)g.grid * g.slice * 16;
             g.on = true;
         }
-    CK(c->d_planes.reserve(planes_bytes));
+    CK(w.d_planes.reserve(planes_bytes));
     for (int lc = 0; lc < NLC; ++lc) {
         if (lc_n[lc] == 0) continue;
         const int NT = LC_NT[lc];
@@ -470,9 +496,9 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             fa.ds = (const long long*)d_ds;
             fa.y = d_y;
             fa.y_dtype = y_dtype;
-            fa.offsets = (const long long*)c->d_offsets.p;
+            fa.offsets = (const long long*)w.d_offsets.p;
             const int q = lc * NQ + rm;
-            fa.q_items = (const int*)c->d_qitems.p + (size_t)q * N;
+            fa.q_items = (const int*)w.d_qitems.p + (size_t)q * N;
             fa.q_count = q_count + q;
             fa.q_head = q_head + q;
             fa.params = d_params;
@@ -485,19 +511,19 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
             fa.pstride = L.pstride;
             fa.Tp = Tp;
             fa.ppad = ppad;
-            fa.planes = (double2*)((char*)c->d_planes.p + g.off);
+            fa.planes = (double2*)((char*)w.d_planes.p + g.off);
             fa.nseas_stride = (int)g.slice;
             fa.theta_in = d_theta_in;
             fa.grad_out = d_grad_out;
             fa.trace = d_trace;
             fa.trace_cap = trace_cap;
-            fa.nq_count = (int*)c->d_nq.p;
-            fa.nq_items = opts->algorithm == PB200_ALG_LBFGS_NEWTON ? (int*)c->d_nq.p + 2 : nullptr;
+            fa.nq_count = (int*)w.d_nq.p;
+            fa.nq_items = opts->algorithm == PB200_ALG_LBFGS_NEWTON ? (int*)w.d_nq.p + 2 : nullptr;
             fa.o = od;
             if (g.grouped) {
-                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, fa, g.grid, c->stream, nullptr));
+                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, fa, g.grid, w.stream, nullptr));
             } else {
-                CK(LAUNCH[mask](NT, opts->growth, reg, fa, g.grid, smem, c->stream, nullptr));
+                CK(LAUNCH[mask](NT, opts->growth, reg, fa, g.grid, smem, w.stream, nullptr));
             }
             c->launches++;
         }
@@ -508,10 +534,10 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         na.ds = (const long long*)d_ds;
         na.y = d_y;
         na.y_dtype = y_dtype;
-        na.offsets = (const long long*)c->d_offsets.p;
-        na.nq_count = (const int*)c->d_nq.p;
-        na.nq_head = (int*)c->d_nq.p + 1;
-        na.nq_items = (const int*)c->d_nq.p + 2;
+        na.offsets = (const long long*)w.d_offsets.p;
+        na.nq_count = (const int*)w.d_nq.p;
+        na.nq_head = (int*)w.d_nq.p + 1;
+        na.nq_items = (const int*)w.d_nq.p + 2;
         na.params = d_params;
         na.tchange = d_tchange;
         na.meta_i32 = d_meta_i32;
@@ -524,7 +550,7 @@ static int fit_impl(pb200_ctx* c, const pb200_options* opts, const int64_t* d_ds
         const size_t nsm = pb200::nw::newton_smem_bytes(L.pstride);
         CK(cudaFuncSetAttribute(pb200::nw::newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsm));
         const int ngrid = (int)std::min<int64_t>(N, opts->algorithm == PB200_ALG_NEWTON ? (int64_t)c->sms * 2 : (int64_t)c->sms);
-        pb200::nw::newton_kernel<<<ngrid, 32 * pb200::nw::NW_WARPS, nsm, c->stream>>>(na);
+        pb200::nw::newton_kernel<<<ngrid, 32 * pb200::nw::NW_WARPS, nsm, w.stream>>>(na);
         CK(cudaGetLastError());
         c->launches++;
     }
@@ -537,7 +563,11 @@ PB200_API int pb200_fit_device(pb200_ctx* c, const pb200_options* opts, const in
                      const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
                      const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
                      int64_t* d_meta_i64, double* d_meta_f64) {
-    return fit_impl(c, opts, d_ds, d_y, y_dtype, h_offsets, n_series, floor, cap_multiplier, d_cap, d_params, d_tchange,
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    CK(cudaSetDevice(c->device));
+    int rc = begin_fit_call(c);
+    if (rc) return rc;
+    return fit_impl(c, c->ws[0], opts, d_ds, d_y, y_dtype, h_offsets, n_series, floor, cap_multiplier, d_cap, d_params, d_tchange,
                     d_meta_i32, d_meta_i64, d_meta_f64, nullptr, nullptr);
 }
 
@@ -569,7 +599,9 @@ PB200_API int pb200_objective_host(pb200_ctx* c, const pb200_options* opts, cons
     CK(cudaMemcpyAsync(c->d_y.p, h_y, (size_t)R * y_elem(y_dtype), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_yhat.p, h_theta, N * L.pstride * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->d_lo.p, 0, N * L.pstride * 8, c->stream));
-    rc = fit_impl(c, opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype, h_offsets, n_series, floor, cap_multiplier,
+    rc = begin_fit_call(c);
+    if (rc) return rc;
+    rc = fit_impl(c, c->ws[0], opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype, h_offsets, n_series, floor, cap_multiplier,
                   nullptr, (double*)c->d_params.p, (double*)c->d_tchange.p, (int32_t*)c->d_mi32.p,
                   (int64_t*)c->d_mi64.p, (double*)c->d_mf64.p, (const double*)c->d_yhat.p, (double*)c->d_lo.p);
     if (rc) return rc;
@@ -604,24 +636,45 @@ PB200_API int pb200_fit_host(pb200_ctx* c, const pb200_options* opts, const int6
     CK(c->d_mi32.reserve(N * 8 * 4));
     CK(c->d_mi64.reserve(N * 2 * 8));
     CK(c->d_mf64.reserve(N * 4 * 8));
-    CK(cudaMemcpyAsync(c->d_ds.p, h_ds, (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_y.p, h_y, (size_t)R * y_elem(y_dtype), cudaMemcpyHostToDevice, c->stream));
-    const double* dcap = nullptr;
-    if (h_cap) {
-        CK(c->d_cap.reserve(N * 8));
-        CK(cudaMemcpyAsync(c->d_cap.p, h_cap, N * 8, cudaMemcpyHostToDevice, c->stream));
-        dcap = (const double*)c->d_cap.p;
-    }
-    rc = pb200_fit_device(c, opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype, h_offsets, n_series, floor,
-                          cap_multiplier, dcap, (double*)c->d_params.p, (double*)c->d_tchange.p, (int32_t*)c->d_mi32.p,
-                          (int64_t*)c->d_mi64.p, (double*)c->d_mf64.p);
+    if (h_cap) CK(c->d_cap.reserve(N * 8));
+    rc = begin_fit_call(c);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h_params, c->d_params.p, N * L.pstride * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_tchange, c->d_tchange.p, N * L.smax * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_meta_i32, c->d_mi32.p, N * 8 * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_meta_i64, c->d_mi64.p, N * 2 * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_meta_f64, c->d_mf64.p, N * 4 * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    // series chunks with (nearly) equal rows, alternating over the two workspaces / streams: copy in, fit, copy out
+    int nch = c->host_chunks;
+    if (n_series < 4096 * (int64_t)nch || R < (int64_t)nch * (1 << 20)) nch = 1;
+    const size_t ye = y_elem(y_dtype);
+    std::vector<int64_t> cut(nch + 1, 0), hoff;
+    cut[nch] = n_series;
+    for (int k = 1; k < nch; ++k)
+        cut[k] = std::lower_bound(h_offsets, h_offsets + n_series + 1, R * k / nch) - h_offsets;
+    for (int k = 0; k < nch; ++k) {
+        const int64_t s0 = cut[k], s1 = cut[k + 1], nk = s1 - s0;
+        if (nk <= 0) continue;
+        FitWs& w = c->ws[k & 1];
+        const int64_t r0 = h_offsets[s0], rk = h_offsets[s1] - r0;
+        CK(cudaMemcpyAsync((char*)c->d_ds.p + (size_t)r0 * 8, h_ds + r0, (size_t)rk * 8, cudaMemcpyHostToDevice, w.stream));
+        CK(cudaMemcpyAsync((char*)c->d_y.p + (size_t)r0 * ye, (const char*)h_y + (size_t)r0 * ye, (size_t)rk * ye,
+                           cudaMemcpyHostToDevice, w.stream));
+        const double* dcap = nullptr;
+        if (h_cap) {
+            CK(cudaMemcpyAsync((double*)c->d_cap.p + s0, h_cap + s0, (size_t)nk * 8, cudaMemcpyHostToDevice, w.stream));
+            dcap = (const double*)c->d_cap.p + s0;
+        }
+        hoff.resize((size_t)nk + 1);
+        for (int64_t i = 0; i <= nk; ++i) hoff[(size_t)i] = h_offsets[s0 + i] - r0;
+        rc = fit_impl(c, w, opts, (const int64_t*)c->d_ds.p + r0, (const char*)c->d_y.p + (size_t)r0 * ye, y_dtype, hoff.data(), nk,
+                      floor, cap_multiplier, dcap, (double*)c->d_params.p + (size_t)s0 * L.pstride,
+                      (double*)c->d_tchange.p + (size_t)s0 * L.smax, (int32_t*)c->d_mi32.p + (size_t)s0 * 8,
+                      (int64_t*)c->d_mi64.p + (size_t)s0 * 2, (double*)c->d_mf64.p + (size_t)s0 * 4, nullptr, nullptr);
+        if (rc) return rc;
+        const size_t n0 = (size_t)s0, nn = (size_t)nk;
+        CK(cudaMemcpyAsync(h_params + n0 * L.pstride, (double*)c->d_params.p + n0 * L.pstride, nn * L.pstride * 8, cudaMemcpyDeviceToHost, w.stream));
+        CK(cudaMemcpyAsync(h_tchange + n0 * L.smax, (double*)c->d_tchange.p + n0 * L.smax, nn * L.smax * 8, cudaMemcpyDeviceToHost, w.stream));
+        CK(cudaMemcpyAsync(h_meta_i32 + n0 * 8, (int32_t*)c->d_mi32.p + n0 * 8, nn * 8 * 4, cudaMemcpyDeviceToHost, w.stream));
+        CK(cudaMemcpyAsync(h_meta_i64 + n0 * 2, (int64_t*)c->d_mi64.p + n0 * 2, nn * 2 * 8, cudaMemcpyDeviceToHost, w.stream));
+        CK(cudaMemcpyAsync(h_meta_f64 + n0 * 4, (double*)c->d_mf64.p + n0 * 4, nn * 4 * 8, cudaMemcpyDeviceToHost, w.stream));
+    }
+    for (FitWs& w : c->ws) CK(cudaStreamSynchronize(w.stream));
     return PB200_OK;
 }
 
@@ -653,7 +706,9 @@ PB200_API int pb200_fit_trace_host(pb200_ctx* c, const pb200_options* opts, cons
     CK(cudaMemcpyAsync(c->d_ds.p, h_ds, (size_t)R * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_y.p, h_y, (size_t)R * y_elem(y_dtype), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(c->d_trace.p, 0, tbytes, c->stream));
-    rc = fit_impl(c, opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype, h_offsets, n_series, floor, cap_multiplier, nullptr,
+    rc = begin_fit_call(c);
+    if (rc) return rc;
+    rc = fit_impl(c, c->ws[0], opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype, h_offsets, n_series, floor, cap_multiplier, nullptr,
                   (double*)c->d_params.p, (double*)c->d_tchange.p, (int32_t*)c->d_mi32.p, (int64_t*)c->d_mi64.p,
                   (double*)c->d_mf64.p, nullptr, nullptr, (double*)c->d_trace.p, trace_cap);
     if (rc) return rc;

@@ -16,8 +16,8 @@
 //   * the groups of a warp run the optimiser's state machine in lockstep at evaluation granularity:
 //     [fetch + stage a series if idle] -> evaluate -> line-search step -> (accepted: update + new direction);
 //     a group whose action differs simply sits out that routine.
-// Data layout per series slot: global workspace: y_scaled as point PAIRS, pair m of lane l at
-// ((m G + l) 2) doubles (a lane's cp.async is 16 B, a group's G lanes read 16 G contiguous bytes), and the
+// Data layout per series slot: global workspace: y_scaled in steps of U points per lane (U = 2; 4 was measured and lost),
+// step m of lane l at ((m G + l) U) doubles (a lane's cp.async is 16 B, a group's G lanes read 8 U G contiguous bytes), and the
 // L-BFGS history Y[5], S[5] (read once per iteration); shared memory (GState): optimiser state, the six
 // working vectors, segment arrays, the seasonal table s_p / R_p.
 // Arithmetic differences from fit_kernel.cuh's day-table variant (parity is to the oracle, 1e-10 / 1e-8):
@@ -56,12 +56,13 @@ struct GState {
 
 template <int G>
 inline size_t group_smem_bytes() {
-    return (size_t)(32 / G) * ((sizeof(GState<G>) + 15) & ~(size_t)15) + (size_t)2 * 32 * 16;   // + cp.async ring
+    return (size_t)(32 / G) * ((sizeof(GState<G>) + 15) & ~(size_t)15) + (size_t)2 * (grp_u(G) / 2) * 32 * 16   // + cp.async ring
+           + sizeof(FitOptsDev);                                                                          // + the options
 }
 // global workspace per series slot (doubles): y pairs, then history Y[5], S[5]
 __host__ __device__ inline size_t group_plane_doubles(int tmax, int G) {
-    const int cmax = (tmax + G - 1) / G + GCHUNK_SLACK;
-    return (size_t)((cmax + 1) / 2) * G * 2 + 8;
+    const int cmax = (tmax + G - 1) / G + GCHUNK_SLACK, U = grp_u(G);
+    return (size_t)((cmax + U - 1) / U) * G * U + 8;
 }
 constexpr int GHIST = 2 * HMAX * GPPAD;
 
@@ -72,6 +73,12 @@ __device__ __forceinline__ GState<G>& gstate(int gi) {
 template <int G>
 __device__ __forceinline__ double2* gring() {
     return reinterpret_cast<double2*>(pb200_smem + (size_t)(32 / G) * ((sizeof(GState<G>) + 15) & ~(size_t)15));
+}
+// the fit options, copied out of the kernel parameters once per warp (the optimiser's routines take them by reference;
+// a reference into the parameter bank would force a local-memory copy that misses L1 on every use: r2c profile)
+template <int G>
+__device__ __forceinline__ FitOptsDev& gopts() {
+    return *reinterpret_cast<FitOptsDev*>(reinterpret_cast<unsigned char*>(gring<G>()) + (size_t)2 * (grp_u(G) / 2) * 32 * 16);
 }
 
 // ---- group collectives (lanes of one series; `gm` is the group's lane mask) ----
@@ -114,7 +121,7 @@ template <int G>
 __device__ __noinline__ double gvdot(const double* a, const double* b, const int P, const int gl, const unsigned gm) {
     double s = 0.0;
 #pragma unroll
-    for (int u = 0; u < GPPAD / G; ++u) {
+    for (int u = 0; u < (GPPAD + G - 1) / G; ++u) {
         const int q = gl + u * G;
         if (q < P) s = fma(a[q], b[q], s);
     }
@@ -255,9 +262,10 @@ struct GPoint {
 // ---------------------------------------------------------------------------------------
 // evaluation, part 2: the pass over the points (all lanes of the warp, every active group)
 // ---------------------------------------------------------------------------------------
-template <int G, bool LOGI, bool MULT>
+template <int G, bool LOGI, bool MULT, int U>
 __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, const bool active, const int gl, const int lane,
                                           const unsigned gm) {
+    static_assert(U == 2 || U == 4, "points per lane per step");
     const int P = active ? s.tabP : GPT, PL = active ? s.tabPL : 0;     // (an idle group's lanes only keep step)
     const double2 rct = *reinterpret_cast<const double2*>(s.rotd);
     const double2 w0 = s.dph[gl];
@@ -265,7 +273,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     if (active) {
         double2 w = w0;
         int p = gl * PL;
-#pragma unroll 1
+#pragma unroll 2
         for (int q = 0; q < PL; ++q, ++p) {
             if (p < P) {
                 double X[GKD];
@@ -296,7 +304,6 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         for (int q = 0; q < S; ++q) j += s.bidx[q] < i0 ? 1 : 0;
     }
     const int j0 = j;
-    if (!active) j = 0;
     double gacc[GK];
 #pragma unroll
     for (int q = 0; q < GK; ++q) gacc[q] = 0.0;
@@ -311,90 +318,107 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         if (erec) e = exp_fastpath(-(kcj * (((double)(i0 - 1)) * h - mcj)));     // at the virtual point before the chunk
     }
     // uniform trip count over the warp: the lanes stay in step for the bin updates
-    int npair = active ? (chunk + 1) >> 1 : 0;
+    int nstep = active ? (chunk + U - 1) / U : 0;
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) npair = max(npair, __shfl_xor_sync(FULL, npair, o));
-    double2* const ring = gring<G>() + lane;                  // stage st: row st (32 double2)
-    const double2* gsrc = reinterpret_cast<const double2*>(plane) + gl;   // pair m of this lane: gsrc[m * G]
-    if (0 < npts) cp_async16<false>(ring, gsrc, 0ull);
+    for (int o = 16; o >= 1; o >>= 1) nstep = max(nstep, __shfl_xor_sync(FULL, nstep, o));
+    // cp.async ring: 2 stages of U points per lane (stage st, half q: row (st (U / 2) + q) of 32 double2)
+    double2* const ring = gring<G>() + lane;
+    const double2* gsrc = reinterpret_cast<const double2*>(plane) + gl * (U / 2);   // step m of this lane: gsrc[m G (U / 2) + q]
+    if (0 < npts) {
+#pragma unroll
+        for (int q = 0; q < U / 2; ++q) cp_async16<false>(ring + q * 32, gsrc + q, 0ull);
+    }
     cp_async_commit();
-    const double2* gnext = gsrc + G;
+    const double2* gnext = gsrc + G * (U / 2);
     int pb = P > 0 ? i0 % P : 0;
     double2 ws = s.wph[gl];
     const double2 rcw = *reinterpret_cast<const double2*>(s.rotw);
     double tn = (double)i0;
 #pragma unroll 1
-    for (int m = 0; m < npair; ++m) {
-        const int n = 2 * m;
-        double2* const cur = ring + (m & 1) * 32;
-        double2* const fill = ring + ((m + 1) & 1) * 32;
-        if (n + 2 < npts) cp_async16<false>(fill, gnext, 0ull);
+    for (int m = 0; m < nstep; ++m) {
+        const int n = U * m;
+        double2* const cur = ring + (m & 1) * (U / 2) * 32;
+        double2* const fill = ring + ((m + 1) & 1) * (U / 2) * 32;
+        if (n + U < npts) {
+#pragma unroll
+            for (int q = 0; q < U / 2; ++q) cp_async16<false>(fill + q * 32, gnext + q, 0ull);
+        }
         cp_async_commit();
-        gnext += G;
+        gnext += G * (U / 2);
         cp_async_wait<1>();
-        const bool va = n < npts, vb = n + 1 < npts;
-        const double2 yy = va ? cur[0] : make_double2(0.0, 0.0);
-        const int pa = pb, pbb = (pa + 1 == P) ? 0 : pa + 1;
-        const double spa = s.stab[pa], spb = s.stab[pbb];
-        const double Ra = s.rtab[pa], Rb = s.rtab[pbb];
-        const int ia = i0 + n, ib = ia + 1;
-        const double ta = tn * h, tb = fma(tn, h, h);
-        tn += 2.0;
-        // exp ratio recurrence: the step INTO a point uses the rate of the segment the previous point is in
-        double ea = 0.0, eb = 0.0;
-        if constexpr (LOGI) ea = e * qj;
-        while (va && ia == nb) {                               // changepoints at point a: partial sums so far
-            s.bndU[j] = locU;
-            s.bndV[j] = locV;
-            ++j;
-            kcj = s.kc[j];
-            mcj = s.mc[j];
-            if constexpr (LOGI) qj = s.qs[j];
-            nb = j < S ? s.bidx[j] : 0x7fffffff;
+        double yv[U];
+        bool val[U];
+        int pu[U], jlo[U + 1];
+        double sp[U], Rv[U], tt[U], ee[U], kcu[U], mcu[U];
+#pragma unroll
+        for (int q = 0; q < U / 2; ++q) {
+            const double2 v = cur[q * 32];
+            yv[2 * q] = v.x;
+            yv[2 * q + 1] = v.y;
         }
-        const double kca = kcj, mca = mcj;
-        const int jmid = j;
-        if constexpr (LOGI) eb = ea * qj;
-        while (vb && ib == nb) {                               // changepoints at point b: recorded once a's share is known
-            ++j;
-            kcj = s.kc[j];
-            mcj = s.mc[j];
-            if constexpr (LOGI) qj = s.qs[j];
-            nb = j < S ? s.bidx[j] : 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            val[u] = n + u < npts;
+            pu[u] = pb;
+            pb = (pb + 1 == P) ? 0 : pb + 1;
+            sp[u] = s.stab[pu[u]];
+            Rv[u] = s.rtab[pu[u]];
+            tt[u] = fma(tn, h, (double)u * h);
         }
+        tn += (double)U;
+        // exp ratio recurrence: the step INTO a point uses the rate of the segment the previous point is in; then the
+        // changepoints AT the point switch rate, offset and ratio (their partial sums are recorded below, once the
+        // contributions of the step's earlier points are known)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if constexpr (LOGI) { e = e * qj; ee[u] = e; }
+            else ee[u] = 0.0;
+            jlo[u] = j;
+            const int iu = i0 + n + u;
+            while (val[u] && iu == nb) {
+                ++j;
+                kcj = s.kc[j];
+                mcj = s.mc[j];
+                if constexpr (LOGI) qj = s.qs[j];
+                nb = j < S ? s.bidx[j] : 0x7fffffff;
+            }
+            kcu[u] = kcj;
+            mcu[u] = mcj;
+        }
+        jlo[U] = j;
         if constexpr (LOGI) {
             if (!erec) {                                       // exponent out of the recurrence's range: direct exp
-                ea = exp_fastpath(-(kca * (ta - mca)));
-                eb = exp_fastpath(-(kcj * (tb - mcj)));
-            }
-            e = eb;
-        }
-        GPoint<LOGI, MULT> A, B;
-        A.run(yy.x, ta, spa, ws, rcw, s.bcoef, ea, kca, mca, cap, va);
-        B.run(yy.y, tb, spb, ws, rcw, s.bcoef, eb, kcj, mcj, cap, vb);
-        ss = fma(A.r, A.r, ss);
-        ss = fma(B.r, B.r, ss);
-        if (va) s.rtab[pa] = Ra + A.cb;                        // R_p += c_i (bins of a step are pairwise distinct)
-        if (vb) s.rtab[pbb] = Rb + B.cb;
 #pragma unroll
-        for (int k = 0; k < GKW; ++k) gacc[k] = fma(B.cb, B.X[k], fma(A.cb, A.X[k], gacc[k]));
-        locU = fma(A.dz, A.tm, locU);
-        locV += A.dz;
-#pragma unroll 1
-        for (int jj = jmid; jj < j; ++jj) {
-            s.bndU[jj] = locU;
-            s.bndV[jj] = locV;
+                for (int u = 0; u < U; ++u) ee[u] = exp_fastpath(-(kcu[u] * (tt[u] - mcu[u])));
+            }
         }
-        locU = fma(B.dz, B.tm, locU);
-        locV += B.dz;
-        pb = (pbb + 1 == P) ? 0 : pbb + 1;
+        GPoint<LOGI, MULT> pt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pt[u].run(yv[u], tt[u], sp[u], ws, rcw, s.bcoef, ee[u], kcu[u], mcu[u], cap, val[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ss = fma(pt[u].r, pt[u].r, ss);
+            if (val[u]) s.rtab[pu[u]] = Rv[u] + pt[u].cb;      // R_p += c_i (bins of a step are pairwise distinct)
+#pragma unroll
+            for (int k = 0; k < GKW; ++k) gacc[k] = fma(pt[u].cb, pt[u].X[k], gacc[k]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll 1
+            for (int jj = jlo[u]; jj < jlo[u + 1]; ++jj) {     // changepoints at point u: sums over the points before it
+                s.bndU[jj] = locU;
+                s.bndV[jj] = locV;
+            }
+            locU = fma(pt[u].dz, pt[u].tm, locU);
+            locV += pt[u].dz;
+        }
         __syncwarp();
     }
     // ---- table features' beta gradient from the residual bins ----
     if (active) {
         double2 w = w0;
         int p = gl * PL;
-#pragma unroll 1
+#pragma unroll 2
         for (int q = 0; q < PL; ++q, ++p) {
             if (p < P) {
                 double X[GKD];
@@ -424,18 +448,19 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     {
         double* scr = s.stab;                                   // stab and rtab are contiguous: 2 GPT doubles
         static_assert(15 * 8 <= 2 * GPT, "reduction scratch");
-        if constexpr (G == 16) {
-            // fold the upper half of the group onto the lower half first
-            if (gl >= 8) {
+        // fold the group's upper blocks of eight lanes onto the lowest block, top block first (fixed order)
 #pragma unroll
-                for (int v = 0; v < GK; ++v) scr[v * 8 + (gl - 8)] = gacc[v];
-                scr[GK * 8 + (gl - 8)] = ss;
+        for (int blk = G / 8 - 1; blk >= 1; --blk) {
+            if (gl >= 8 * blk && gl < 8 * blk + 8) {
+#pragma unroll
+                for (int v = 0; v < GK; ++v) scr[v * 8 + (gl - 8 * blk)] = gacc[v];
+                scr[GK * 8 + (gl - 8 * blk)] = ss;
             }
             __syncwarp();
-            if (gl < 8) {
+            if (gl >= 8 * blk - 8 && gl < 8 * blk) {
 #pragma unroll
-                for (int v = 0; v < GK; ++v) gacc[v] += scr[v * 8 + gl];
-                ss += scr[GK * 8 + gl];
+                for (int v = 0; v < GK; ++v) gacc[v] += scr[v * 8 + (gl - (8 * blk - 8))];
+                ss += scr[GK * 8 + (gl - (8 * blk - 8))];
             }
             __syncwarp();
         }
@@ -445,11 +470,11 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
             scr[GK * 8 + gl] = ss;
         }
         __syncwarp();
-        // lane v (< 15, or v and v + 8 when G == 8) adds up the eight partials of value v into bnd-independent slots
+        // lane v (< 15; v and v + 8 when G == 8) adds up the eight partials of value v
         double t0 = 0.0, t1 = 0.0;
         if (gl < 15) {
             const int v = gl;
-            if (G == 16 || v < 8) {
+            if (G >= 16 || v < 8) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) t0 += scr[v * 8 + q];
             }
@@ -461,7 +486,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         __syncwarp();
         // totals: value v in scr[v] (v = 0..14)
         if (active) {
-            if (G == 16) { if (gl < 15) scr[gl] = t0; }
+            if (G >= 16) { if (gl < 15) scr[gl] = t0; }
             else { scr[gl] = t0; if (gl + 8 < 15) scr[gl + 8] = t1; }
         }
         __syncwarp();
@@ -627,7 +652,7 @@ __device__ __noinline__ void g_make_trial(GState<G>& s, const double alpha, cons
     const double* p = s.vec[s.ls.ip];
     double* xt = s.vec[s.ls.ixt];
 #pragma unroll
-    for (int u = 0; u < GPPAD / G; ++u) {
+    for (int u = 0; u < (GPPAD + G - 1) / G; ++u) {
         const int q = gl + u * G;
         if (q < P) xt[q] = x[q] + alpha * p[q];
     }
@@ -642,7 +667,7 @@ __device__ __noinline__ void g_ls_begin(GState<G>& s, const int gl, const unsign
     double* p = s.vec[ls.ip];
     if (ls.resetB) {
 #pragma unroll
-        for (int u = 0; u < GPPAD / G; ++u) {
+        for (int u = 0; u < (GPPAD + G - 1) / G; ++u) {
             const int q = gl + u * G;
             if (q < P) p[q] = -g[q];
         }
@@ -764,7 +789,7 @@ __device__ __noinline__ int g_ls_step(GState<G>& s, const int gl, const unsigned
 template <int G>
 __device__ __noinline__ int g_post_accept(GState<G>& s, double* hist, const int gl, const unsigned gm, const int P,
                                           const FitOptsDev& o, double* trace, const int trace_cap) {
-    constexpr int NV = GPPAD / G;
+    constexpr int NV = (GPPAD + G - 1) / G;
     LSState& ls = s.ls;
     double* HY = hist;
     double* HS = hist + HMAX * GPPAD;
@@ -927,7 +952,7 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
     const long long off = a.offsets[sidx];
     const long long step = a.ds[off + 1] - a.ds[off];
     const int tabP = (int)((86400LL * 1000000000LL) / step);
-    const int chunk = grp_chunk(T, tabP, G);
+    const int chunk = grp_chunk(T, tabP, G, grp_u(G));
     const double dts = (double)tscale;
     const double cap_s = LOGI ? (capv - fl) / y_scale : 0.0;
     const int PL = (tabP + G - 1) / G;
@@ -952,8 +977,9 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
 #pragma unroll 1
     for (int i = gl; i < T; i += G) {
         const double yv = load_y(a.y, a.y_dtype, off + i);
+        constexpr int U = grp_u(G);
         const int own = i / chunk, n = i - own * chunk;
-        plane[((size_t)(n >> 1) * G + own) * 2 + (n & 1)] = (yv - fl) / y_scale;
+        plane[((size_t)(n / U) * G + own) * U + (n % U)] = (yv - fl) / y_scale;
     }
     // ---- per-lane start phases: weekly angle at the lane's first point, daily angle at its first table phase ----
     {
@@ -1074,6 +1100,7 @@ __device__ __noinline__ void g_write_record(GState<G>& s, const FitArgs& a, cons
 // ---------------------------------------------------------------------------------------
 template <int G, bool LOGI, bool MULT>
 __global__ void __launch_bounds__(32, G == 8 ? 8 : 16) fit_group_kernel(const FitArgs a) {
+    static_assert(G == 8 || G == 16 || G == 32, "lanes per series");
     constexpr int NSER = 32 / G;
     const int lane = threadIdx.x & 31, gi = lane / G, gl = lane % G;
     const unsigned gm = G == 32 ? FULL : (((1u << G) - 1u) << (gi * G));
@@ -1084,7 +1111,11 @@ __global__ void __launch_bounds__(32, G == 8 ? 8 : 16) fit_group_kernel(const Fi
     double* const trace_base = a.trace;
     const double tau = a.o.tau, rtau = a.o.rtau, inv_seas2 = a.o.inv_seas2;
     if (gl == 0) { s.state = ST_IDLE; s.series = -1; }
+    if (lane == 0) gopts<G>() = a.o;
     __syncwarp();
+    const FitOptsDev& opt = gopts<G>();
+    const double init_alpha = a.o.init_alpha;
+    const int trace_cap = a.trace_cap;
     bool exhausted = false;
     for (;;) {
         // ---- idle groups take the next series of the queue ----
@@ -1119,7 +1150,7 @@ __global__ void __launch_bounds__(32, G == 8 ? 8 : 16) fit_group_kernel(const Fi
             if (gl == 0) s.ls.nevals += 1;
         }
         __syncwarp();
-        g_point_pass<G, LOGI, MULT>(s, plane, active, gl, lane, gm);
+        g_point_pass<G, LOGI, MULT, grp_u(G)>(s, plane, active, gl, lane, gm);
         __syncwarp();
         int err = 0;
         if (active) err = g_eval_finalize<G, LOGI>(s, s.vec[ixv], s.vec[igv], gl, gm, tau, rtau, inv_seas2, first ? &s.ls.fk : &s.ls.ft);
@@ -1153,8 +1184,8 @@ __global__ void __launch_bounds__(32, G == 8 ? 8 : 16) fit_group_kernel(const Fi
         }
         __syncwarp();
         if (act == ACT_ACCEPT) {
-            double* tr = trace_base ? trace_base + (size_t)s.series * a.trace_cap * 4 : nullptr;
-            status = g_post_accept<G>(s, hist, gl, gm, P, a.o, tr, a.trace_cap);
+            double* tr = trace_base ? trace_base + (size_t)s.series * trace_cap * 4 : nullptr;
+            status = g_post_accept<G>(s, hist, gl, gm, P, opt, tr, trace_cap);
             if (status != PB200_ST_SUCCESS) done = true;
             else {
                 if (gl == 0) { s.ls.iters += 1; s.ls.resetB = 0; }
@@ -1163,7 +1194,7 @@ __global__ void __launch_bounds__(32, G == 8 ? 8 : 16) fit_group_kernel(const Fi
             }
         }
         __syncwarp();
-        if (act == ACT_FAIL + 1) g_ls_begin<G>(s, gl, gm, P, a.o.init_alpha);
+        if (act == ACT_FAIL + 1) g_ls_begin<G>(s, gl, gm, P, init_alpha);
         __syncwarp();
         if (done) {
             g_write_record<G>(s, a, status, gl, gm);

@@ -1,4 +1,4 @@
-// Instantiations of the grouped-lanes fit kernel (fit_group.cuh): G in {8, 16} lanes per series x growth x
+// Instantiations of the grouped-lanes fit kernel (fit_group.cuh): G in {8, 16, 32} lanes per series x growth x
 // seasonality mode, for the weekly + daily day-table class.
 #include "fit_group.cuh"
 #include "launch.h"
@@ -25,6 +25,7 @@ static cudaError_t launch_group_g(int logi, int mult, const FitArgs& a, int grid
 cudaError_t launch_fit_group(int g, int logi, int mult, const FitArgs& a, int grid, cudaStream_t st, int* occ) {
     if (g == 8) return launch_group_g<8>(logi, mult, a, grid, st, occ);
     if (g == 16) return launch_group_g<16>(logi, mult, a, grid, st, occ);
+    if (g == 32) return launch_group_g<32>(logi, mult, a, grid, st, occ);
     return cudaErrorInvalidValue;
 }
 

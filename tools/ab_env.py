@@ -1,5 +1,5 @@
 """Dev helper: config-3 fit under several context environments in one process (same inputs), e.g.
-    python tools/ab_env.py 50000 3 g8: g16:PB200_GROUP=16 tab32:PB200_GROUP=0 notab:PB200_NO_TAB=1
+    python tools/ab_env.py 50000 3 g8: g16:PB200_GROUP=16 g32:PB200_GROUP=32 tab32:PB200_GROUP=0 notab:PB200_NO_TAB=1
 prints timings, the kernel-variant counts and how the results compare with the first configuration."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
