@@ -112,6 +112,8 @@ struct pb200_ctx {
     bool tab_on = true;    // PB200_NO_TAB=1 disables the seasonal-table variants (A/B runs)
     int grp_g = 8;         // lanes per series of the grouped day-table kernel (fit_group.cuh); PB200_GROUP=0|8|16, 0 = point_pass_tab
     DevBuf d_trace;        // trajectory rows of pb200_fit_trace_host
+    int grp_min = 16384;   // PB200_GROUP_MIN: smallest batch the grouped kernel takes (below it its 4-series warps leave a longer
+                           // straggler tail than one warp per series: r2e, 6250 series: 105 vs 80 ms; 50k: 419 vs 470 ms)
     int host_chunks = 4;   // PB200_HOST_CHUNKS: series chunks of pb200_fit_host (1 = no overlap)
 };
 
@@ -266,6 +268,7 @@ PB200_API pb200_ctx* pb200_create(int device) {
     c->tab_on = env_int("PB200_NO_TAB", 0) == 0;
     c->grp_g = env_int("PB200_GROUP", 8);
     if (c->grp_g != 8 && c->grp_g != 16 && c->grp_g != 32) c->grp_g = 0;
+    c->grp_min = env_int("PB200_GROUP_MIN", 16384);
     return c;
 }
 
@@ -327,7 +330,7 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
                     const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
                     const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
                     int64_t* d_meta_i64, double* d_meta_f64, const double* d_theta_in, double* d_grad_out,
-                    double* d_trace = nullptr, int trace_cap = 0) {
+                    double* d_trace = nullptr, int trace_cap = 0, int64_t n_call = 0) {
     if (!c) return fail(PB200_E_ARG, "ctx is null");
     int rc = check_opts(opts);
     if (rc) return rc;
@@ -400,6 +403,9 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
     int* q_head = q_count + NLC * NQ;
 
     const FitOptsDev od = to_dev(opts);
+    // the grouped day-table kernel takes big batches; with the CTA width pinned (tests, A/B runs) it is not second-guessed
+    // (n_call: series of the whole API call when this is one chunk of it)
+    const int grp_g = (c->tab_on && (!c->lc_auto || std::max<int64_t>(N, n_call) >= c->grp_min)) ? c->grp_g : 0;
     // ---- prep kernel ----
     {
         pb200::PrepArgs pa;
@@ -422,7 +428,7 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
         pa.tab_lc_mask = 0;
         for (int lc = 0; lc < NLC; ++lc)
             if (c->tab_on && LC_NT[lc] == 32) pa.tab_lc_mask |= 1 << lc;
-        pa.grp_g = c->tab_on ? c->grp_g : 0;
+        pa.grp_g = grp_g;
         pa.newton_only = (opts->algorithm == PB200_ALG_NEWTON && !d_theta_in) ? 1 : 0;
         pa.nq_count = (int*)w.d_nq.p;
         pa.nq_items = (int*)w.d_nq.p + 2;
@@ -437,7 +443,6 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
     // ---- fit kernels: one persistent launch per (length class, seasonality class) ----
     // pass 1: launch geometry and the planes workspace (one slice per resident CTA)
     struct Geo { int grid, Tp, ppad; size_t smem, slice, off; bool on, grouped; };
-    const int grp_g = c->tab_on ? c->grp_g : 0;
     Geo geo[NLC][NQ];       // [length class][variant * 8 + seasonality class]
     size_t planes_bytes = 0;
     for (int lc = 0; lc < NLC; ++lc)
@@ -665,7 +670,8 @@ PB200_API int pb200_fit_host(pb200_ctx* c, const pb200_options* opts, const int6
         rc = fit_impl(c, w, opts, (const int64_t*)c->d_ds.p + r0, (const char*)c->d_y.p + (size_t)r0 * ye, y_dtype, hoff.data(), nk,
                       floor, cap_multiplier, dcap, (double*)c->d_params.p + (size_t)s0 * L.pstride,
                       (double*)c->d_tchange.p + (size_t)s0 * L.smax, (int32_t*)c->d_mi32.p + (size_t)s0 * 8,
-                      (int64_t*)c->d_mi64.p + (size_t)s0 * 2, (double*)c->d_mf64.p + (size_t)s0 * 4, nullptr, nullptr);
+                      (int64_t*)c->d_mi64.p + (size_t)s0 * 2, (double*)c->d_mf64.p + (size_t)s0 * 4, nullptr, nullptr, nullptr, 0,
+                      n_series);
         if (rc) return rc;
         const size_t n0 = (size_t)s0, nn = (size_t)nk;
         CK(cudaMemcpyAsync(h_params + n0 * L.pstride, (double*)c->d_params.p + n0 * L.pstride, nn * L.pstride * 8, cudaMemcpyDeviceToHost, w.stream));

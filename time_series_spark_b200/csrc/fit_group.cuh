@@ -27,6 +27,8 @@
 //     only the ratio changes there); one true exp per lane per evaluation.  Evaluations whose exponent
 //     leaves +-600 anywhere (wild line-search trials) take the direct-exp path.
 #pragma once
+#include <type_traits>
+
 #include "fit_kernel.cuh"
 
 namespace pb200 {
@@ -49,6 +51,7 @@ struct GState {
     alignas(16) double rotd[2];          // ... of the daily angle
     alignas(16) double stab[GPT];        // s_p: daily part of X beta at table phase p
     alignas(16) double rtab[GPT];        // R_p: residual bins; stab / rtab double as the reduction scratch
+    int j0l[G];                          // trend segment of the point before each lane's chunk
     double2 wph[G];                      // weekly (sin, cos) at each lane's first point
     double2 dph[G];                      // daily (sin, cos) at each lane's first table phase
     alignas(16) double vec[6][GPPAD];    // x g p x_trial g_trial p_prev (roles in ls.ix ...)
@@ -79,6 +82,10 @@ __device__ __forceinline__ double2* gring() {
 template <int G>
 __device__ __forceinline__ FitOptsDev& gopts() {
     return *reinterpret_cast<FitOptsDev*>(reinterpret_cast<unsigned char*>(gring<G>()) + (size_t)2 * (grp_u(G) / 2) * 32 * 16);
+}
+
+__device__ __forceinline__ void cp_async16_sa(const unsigned smem_addr, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(__cvta_generic_to_global(gsrc)) : "memory");
 }
 
 // ---- group collectives (lanes of one series; `gm` is the group's lane mask) ----
@@ -223,7 +230,7 @@ struct GPoint {
     double X[GKW];
     double r, cb, dz, tm;
     __device__ __forceinline__ void run(const double y, const double t, const double sp, double2& ws, const double2 rcw,
-                                        const double* bcoef, const double e, const double kcj, const double mcj,
+                                        const double (&bcoef)[GKW], const double e, const double kcj, const double mcj,
                                         const double cap, const bool valid) {
         harmonics<3>(ws, X);
         {
@@ -234,9 +241,8 @@ struct GPoint {
         double dot = sp, d1 = 0.0;
 #pragma unroll
         for (int k = 0; k < GKW; k += 2) {
-            const double2 b = *reinterpret_cast<const double2*>(&bcoef[k]);
-            dot = fma(b.x, X[k], dot);
-            d1 = fma(b.y, X[k + 1], d1);
+            dot = fma(bcoef[k], X[k], dot);
+            d1 = fma(bcoef[k + 1], X[k + 1], d1);
         }
         dot += d1;
         double g, sig = 0.0;
@@ -298,11 +304,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     const int i0 = active ? (gl * chunk < T ? gl * chunk : T) : 0;
     const int i1 = active ? (i0 + chunk < T ? i0 + chunk : T) : 0;
     const int npts = i1 - i0;
-    int j = 0;
-    if (active) {
-#pragma unroll 1
-        for (int q = 0; q < S; ++q) j += s.bidx[q] < i0 ? 1 : 0;
-    }
+    int j = active ? s.j0l[gl] : 0;                    // trend segment of the point before the chunk (set by g_fetch)
     const int j0 = j;
     double gacc[GK];
 #pragma unroll
@@ -317,31 +319,48 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     if constexpr (LOGI) {
         if (erec) e = exp_fastpath(-(kcj * (((double)(i0 - 1)) * h - mcj)));     // at the virtual point before the chunk
     }
-    // uniform trip count over the warp: the lanes stay in step for the bin updates
+    // uniform trip counts over the warp (the lanes stay in step for the bin updates): nstep steps in all, the first
+    // nfull of them complete for every lane that has points -- those run without per-point validity tests
     int nstep = active ? (chunk + U - 1) / U : 0;
+    int nfull = active ? npts / U : 0x7fffffff;
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) nstep = max(nstep, __shfl_xor_sync(FULL, nstep, o));
-    // cp.async ring: 2 stages of U points per lane (stage st, half q: row (st (U / 2) + q) of 32 double2)
+    for (int o = 16; o >= 1; o >>= 1) {
+        nstep = max(nstep, __shfl_xor_sync(FULL, nstep, o));
+        nfull = min(nfull, __shfl_xor_sync(FULL, nfull, o));
+    }
+    nfull = min(nfull, nstep);
+    // cp.async ring: 2 stages of U points per lane (stage st, half q: row (st (U / 2) + q) of 32 double2).  The 32-bit
+    // shared-window address is taken once: inside the loop the generic-to-shared conversion cost an S2R per step (r2c profile)
     double2* const ring = gring<G>() + lane;
+    const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
+    constexpr unsigned STAGE_B = (U / 2) * 32 * 16;
     const double2* gsrc = reinterpret_cast<const double2*>(plane) + gl * (U / 2);   // step m of this lane: gsrc[m G (U / 2) + q]
     if (0 < npts) {
 #pragma unroll
-        for (int q = 0; q < U / 2; ++q) cp_async16<false>(ring + q * 32, gsrc + q, 0ull);
+        for (int q = 0; q < U / 2; ++q) cp_async16_sa(ring_sa + q * 512, gsrc + q);
     }
     cp_async_commit();
     const double2* gnext = gsrc + G * (U / 2);
     int pb = P > 0 ? i0 % P : 0;
     double2 ws = s.wph[gl];
     const double2 rcw = *reinterpret_cast<const double2*>(s.rotw);
-    double tn = (double)i0;
-#pragma unroll 1
-    for (int m = 0; m < nstep; ++m) {
+    // weekly coefficients in registers (loop invariant; as shared-memory operands they were re-read every step because
+    // the bin stores may alias them as far as the compiler can tell)
+    double bw[GKW];
+#pragma unroll
+    for (int k = 0; k < GKW; ++k) bw[k] = s.bcoef[k];
+    double tt[U];                                       // t of the step's points, advanced by U h per step
+#pragma unroll
+    for (int u = 0; u < U; ++u) tt[u] = (double)(i0 + u) * h;
+    const double hU = (double)U * h;
+    auto step = [&](const int m, auto checked_tag) {
+        constexpr bool CHECK = decltype(checked_tag)::value;
         const int n = U * m;
         double2* const cur = ring + (m & 1) * (U / 2) * 32;
-        double2* const fill = ring + ((m + 1) & 1) * (U / 2) * 32;
+        const unsigned fill_sa = ring_sa + ((m + 1) & 1) * STAGE_B;
         if (n + U < npts) {
 #pragma unroll
-            for (int q = 0; q < U / 2; ++q) cp_async16<false>(fill + q * 32, gnext + q, 0ull);
+            for (int q = 0; q < U / 2; ++q) cp_async16_sa(fill_sa + q * 512, gnext + q);
         }
         cp_async_commit();
         gnext += G * (U / 2);
@@ -349,7 +368,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         double yv[U];
         bool val[U];
         int pu[U], jlo[U + 1];
-        double sp[U], Rv[U], tt[U], ee[U], kcu[U], mcu[U];
+        double sp[U], Rv[U], ee[U], kcu[U], mcu[U];
 #pragma unroll
         for (int q = 0; q < U / 2; ++q) {
             const double2 v = cur[q * 32];
@@ -358,34 +377,44 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            val[u] = n + u < npts;
+            val[u] = CHECK ? n + u < npts : true;
             pu[u] = pb;
             pb = (pb + 1 == P) ? 0 : pb + 1;
             sp[u] = s.stab[pu[u]];
             Rv[u] = s.rtab[pu[u]];
-            tt[u] = fma(tn, h, (double)u * h);
         }
-        tn += (double)U;
         // exp ratio recurrence: the step INTO a point uses the rate of the segment the previous point is in; then the
-        // changepoints AT the point switch rate, offset and ratio (their partial sums are recorded below, once the
-        // contributions of the step's earlier points are known)
+        // changepoints AT the point switch rate, offset and ratio.  Nearly all steps hold no changepoint of this lane:
+        // one test, and one divergent region for the steps that do (their partial sums are recorded after the
+        // step's arithmetic, when the contributions of the step's earlier points are known)
+        jlo[0] = j;
+        if (nb >= i0 + n + U) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if constexpr (LOGI) { e = e * qj; ee[u] = e; }
-            else ee[u] = 0.0;
-            jlo[u] = j;
-            const int iu = i0 + n + u;
-            while (val[u] && iu == nb) {
-                ++j;
-                kcj = s.kc[j];
-                mcj = s.mc[j];
-                if constexpr (LOGI) qj = s.qs[j];
-                nb = j < S ? s.bidx[j] : 0x7fffffff;
+            for (int u = 0; u < U; ++u) {
+                if constexpr (LOGI) { e = e * qj; ee[u] = e; }
+                else ee[u] = 0.0;
+                kcu[u] = kcj;
+                mcu[u] = mcj;
+                jlo[u + 1] = j;
             }
-            kcu[u] = kcj;
-            mcu[u] = mcj;
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if constexpr (LOGI) { e = e * qj; ee[u] = e; }
+                else ee[u] = 0.0;
+                const int iu = i0 + n + u;
+                while (val[u] && iu == nb) {
+                    ++j;
+                    kcj = s.kc[j];
+                    mcj = s.mc[j];
+                    if constexpr (LOGI) qj = s.qs[j];
+                    nb = j < S ? s.bidx[j] : 0x7fffffff;
+                }
+                kcu[u] = kcj;
+                mcu[u] = mcj;
+                jlo[u + 1] = j;
+            }
         }
-        jlo[U] = j;
         if constexpr (LOGI) {
             if (!erec) {                                       // exponent out of the recurrence's range: direct exp
 #pragma unroll
@@ -394,7 +423,9 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         }
         GPoint<LOGI, MULT> pt[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) pt[u].run(yv[u], tt[u], sp[u], ws, rcw, s.bcoef, ee[u], kcu[u], mcu[u], cap, val[u]);
+        for (int u = 0; u < U; ++u) pt[u].run(yv[u], tt[u], sp[u], ws, rcw, bw, ee[u], kcu[u], mcu[u], cap, val[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) tt[u] += hU;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             ss = fma(pt[u].r, pt[u].r, ss);
@@ -402,18 +433,33 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
 #pragma unroll
             for (int k = 0; k < GKW; ++k) gacc[k] = fma(pt[u].cb, pt[u].X[k], gacc[k]);
         }
+        double preU[U + 1], preV[U + 1];
+        preU[0] = locU;
+        preV[0] = locV;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            preU[u + 1] = fma(pt[u].dz, pt[u].tm, preU[u]);
+            preV[u + 1] = preV[u] + pt[u].dz;
+        }
+        locU = preU[U];
+        locV = preV[U];
+        if (jlo[U] != jlo[0]) {                                  // changepoints at point u: sums over the points before it
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
 #pragma unroll 1
-            for (int jj = jlo[u]; jj < jlo[u + 1]; ++jj) {     // changepoints at point u: sums over the points before it
-                s.bndU[jj] = locU;
-                s.bndV[jj] = locV;
+                for (int jj = jlo[u]; jj < jlo[u + 1]; ++jj) {
+                    s.bndU[jj] = preU[u];
+                    s.bndV[jj] = preV[u];
+                }
             }
-            locU = fma(pt[u].dz, pt[u].tm, locU);
-            locV += pt[u].dz;
         }
         __syncwarp();
-    }
+    };
+    int m = 0;
+#pragma unroll 1
+    for (; m < nfull; ++m) step(m, std::false_type{});
+#pragma unroll 1
+    for (; m < nstep; ++m) step(m, std::true_type{});
     // ---- table features' beta gradient from the residual bins ----
     if (active) {
         double2 w = w0;
@@ -1018,6 +1064,14 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
     }
 #pragma unroll 1
     for (int q = S + gl; q < a.smax; q += G) a.tchange[(size_t)sidx * a.smax + q] = 0.0;
+    __syncwarp(gm);
+    {
+        const int i0 = gl * chunk < T ? gl * chunk : T;
+        int j0 = 0;
+#pragma unroll 1
+        for (int q = 0; q < S; ++q) j0 += s.bidx[q] < i0 ? 1 : 0;
+        s.j0l[gl] = j0;
+    }
     // ---- initial point: Prophet.{linear,logistic}_growth_init + stan_init ----
     {
         const int P = S + GK + 3;
