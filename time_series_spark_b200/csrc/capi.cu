@@ -82,23 +82,27 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-// Everything one in-flight fit call needs besides its inputs and outputs.  Two of them: the *_host entry point cuts
-// a big batch into series chunks and alternates them over the two (stream, workspace) pairs, so that the H2D copy of
-// chunk i + 1 overlaps the fit of chunk i and chunk i + 1's kernels fill the SMs chunk i's stragglers leave idle.
+// Everything one in-flight fit call needs besides its inputs and outputs.  NWS of them: the *_host entry point cuts
+// a big batch into series chunks, one (stream, workspace) pair each, so that the H2D copy of chunk i + 1 overlaps the
+// fit of chunk i and the later chunks' kernels fill the SMs an earlier chunk's stragglers leave idle.  (With two
+// pairs chunk i + 2 had to wait for chunk i's LAST series before it could start: r2i, e2e / value 0.86.)
 struct FitWs {
     cudaStream_t stream = nullptr;
     cudaEvent_t ctl_ev = nullptr;   // recorded after the H2D copies out of h_ctl
     bool ctl_pending = false;
     DevBuf d_offsets, d_order, d_lenclass, d_qitems, d_qctl;   // control workspace (device)
+    DevBuf d_qkey, d_qhist;         // counting sort of the work queues by expected cost (prep_kernel, queue_*_kernel)
     DevBuf d_nq;                    // [0] count, [1] head, [2..] series whose L-BFGS failed its line search (Newton retry queue)
     DevBuf d_planes;                // fit kernels' per-series workspace (one slice per resident CTA / series slot)
     HostBuf h_ctl;                  // pinned staging for offsets / order / lenclass
 };
 
+constexpr int NWS = 4;
+
 struct pb200_ctx {
     int device = 0;
     int sms = 0;
-    FitWs ws[2];
+    FitWs ws[NWS];
     cudaStream_t stream = nullptr;  // = ws[0].stream: the stream of every single-workspace call
     cudaEvent_t fork_ev = nullptr;
     int64_t launches = 0;
@@ -112,6 +116,7 @@ struct pb200_ctx {
     bool tab_on = true;    // PB200_NO_TAB=1 disables the seasonal-table variants (A/B runs)
     int grp_g = 8;         // lanes per series of the grouped day-table kernel (fit_group.cuh); PB200_GROUP=0|8|16, 0 = point_pass_tab
     DevBuf d_trace;        // trajectory rows of pb200_fit_trace_host
+    DevBuf d_nq_all, d_offsets_full;   // pb200_fit_host: per-chunk Newton retry queues, the call's offsets on the device
     int grp_min = 16384;   // PB200_GROUP_MIN: smallest batch the grouped kernel takes (below it its 4-series warps leave a longer
                            // straggler tail than one warp per series: r2e, 6250 series: 105 vs 80 ms; 50k: 419 vs 470 ms)
     int host_chunks = 4;   // PB200_HOST_CHUNKS: series chunks of pb200_fit_host (1 = no overlap)
@@ -260,7 +265,7 @@ PB200_API pb200_ctx* pb200_create(int device) {
         return nullptr;
     }
     c->stream = c->ws[0].stream;
-    c->host_chunks = std::max(1, std::min(16, env_int("PB200_HOST_CHUNKS", 4)));
+    c->host_chunks = std::max(1, std::min(16, env_int("PB200_HOST_CHUNKS", NWS)));
     c->lc_max[0] = env_int("PB200_LC0_MAX", 1 << 30);   // warp-per-series for every length
     c->lc_max[1] = env_int("PB200_LC1_MAX", 1 << 30);
     c->lc_max[2] = 1 << 30;
@@ -277,10 +282,12 @@ PB200_API void pb200_destroy(pb200_ctx* c) {
     cudaSetDevice(c->device);
     for (FitWs& w : c->ws) cudaStreamSynchronize(w.stream);
     for (DevBuf* b : {&c->d_ds, &c->d_y, &c->d_cap, &c->d_params, &c->d_tchange, &c->d_mi32, &c->d_mi64, &c->d_mf64, &c->d_fut,
-                      &c->d_floor, &c->d_yhat, &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc, &c->d_trace, &c->d_vcount})
+                      &c->d_floor, &c->d_yhat, &c->d_lo, &c->d_hi, &c->d_yint, &c->d_mc, &c->d_trace, &c->d_vcount, &c->d_nq_all,
+                      &c->d_offsets_full})
         b->release();
     for (FitWs& w : c->ws) {
-        for (DevBuf* b : {&w.d_offsets, &w.d_order, &w.d_lenclass, &w.d_qitems, &w.d_qctl, &w.d_nq, &w.d_planes}) b->release();
+        for (DevBuf* b : {&w.d_offsets, &w.d_order, &w.d_lenclass, &w.d_qitems, &w.d_qctl, &w.d_nq, &w.d_planes, &w.d_qkey, &w.d_qhist})
+            b->release();
         w.h_ctl.release();
         cudaEventDestroy(w.ctl_ev);
         cudaStreamDestroy(w.stream);
@@ -317,12 +324,46 @@ PB200_API int pb200_synchronize(pb200_ctx* c) {
 
 }  // extern "C"
 
-// zero the per-call variant counters (on workspace 0's stream; workspace 1 is ordered behind it)
+// zero the per-call variant counters (on workspace 0's stream; the other workspaces are ordered behind it)
 static int begin_fit_call(pb200_ctx* c) {
     CK(c->d_vcount.reserve(NQ * 4));
     CK(cudaMemsetAsync(c->d_vcount.p, 0, NQ * 4, c->ws[0].stream));
     CK(cudaEventRecord(c->fork_ev, c->ws[0].stream));
-    CK(cudaStreamWaitEvent(c->ws[1].stream, c->fork_ev, 0));
+    for (int i = 1; i < NWS; ++i) CK(cudaStreamWaitEvent(c->ws[i].stream, c->fork_ev, 0));
+    return PB200_OK;
+}
+
+// newton_kernel over the queue {count, head, items...} at d_nq (16-warp CTAs with ~100 KB of shared memory: they do not
+// fit beside a full house of fit CTAs, which is why the chunked host path runs them after all chunks, and only if needed)
+static int launch_newton(pb200_ctx* c, cudaStream_t st, const pb200_options* opts, const int64_t* d_ds, const void* d_y,
+                         int32_t y_dtype, const int64_t* d_offsets, int64_t n_series, int* d_nq, double* d_params,
+                         double* d_tchange, int32_t* d_meta_i32, int64_t* d_meta_i64, double* d_meta_f64) {
+    pb200_layout L;
+    pb200_get_layout(opts, &L);
+    if (opts->algorithm == PB200_ALG_LBFGS || L.pstride > pb200::nw::NW_PMAX) return PB200_OK;
+    pb200::nw::NewtonArgs na;
+    na.ds = (const long long*)d_ds;
+    na.y = d_y;
+    na.y_dtype = y_dtype;
+    na.offsets = (const long long*)d_offsets;
+    na.nq_count = d_nq;
+    na.nq_head = d_nq + 1;
+    na.nq_items = d_nq + 2;
+    na.params = d_params;
+    na.tchange = d_tchange;
+    na.meta_i32 = d_meta_i32;
+    na.meta_i64 = (const long long*)d_meta_i64;
+    na.meta_f64 = d_meta_f64;
+    na.smax = L.smax;
+    na.kmax = L.kmax;
+    na.pstride = L.pstride;
+    na.o = to_dev(opts);
+    const size_t nsm = pb200::nw::newton_smem_bytes(L.pstride);
+    CK(cudaFuncSetAttribute(pb200::nw::newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsm));
+    const int ngrid = (int)std::min<int64_t>(n_series, opts->algorithm == PB200_ALG_NEWTON ? (int64_t)c->sms * 2 : (int64_t)c->sms);
+    pb200::nw::newton_kernel<<<ngrid, 32 * pb200::nw::NW_WARPS, nsm, st>>>(na);
+    CK(cudaGetLastError());
+    c->launches++;
     return PB200_OK;
 }
 
@@ -330,7 +371,9 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
                     const int64_t* h_offsets, int64_t n_series, double floor, double cap_multiplier,
                     const double* d_cap, double* d_params, double* d_tchange, int32_t* d_meta_i32,
                     int64_t* d_meta_i64, double* d_meta_f64, const double* d_theta_in, double* d_grad_out,
-                    double* d_trace = nullptr, int trace_cap = 0, int64_t n_call = 0) {
+                    double* d_trace = nullptr, int trace_cap = 0, int64_t n_call = 0, int* ext_nq = nullptr) {
+    // ext_nq (chunked host call): {count, head} of this chunk's Newton retry queue followed at ext_nq + 2 by its items;
+    // the queue is then only FILLED here and the caller launches newton_kernel after all chunks (see pb200_fit_host)
     if (!c) return fail(PB200_E_ARG, "ctx is null");
     int rc = check_opts(opts);
     if (rc) return rc;
@@ -389,8 +432,16 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
     CK(w.d_lenclass.reserve((size_t)N * 4));
     CK(w.d_qitems.reserve((size_t)NLC * NQ * N * 4));
     CK(w.d_qctl.reserve((size_t)NLC * NQ * 2 * 4));
-    CK(w.d_nq.reserve((size_t)(N + 2) * 4));                 // count, head, items[N]
-    CK(cudaMemsetAsync(w.d_nq.p, 0, 8, w.stream));
+    CK(w.d_qkey.reserve((size_t)N * 4));
+    CK(w.d_qhist.reserve((size_t)NLC * NQ * pb200::QBINS * 4));
+    CK(cudaMemsetAsync(w.d_qkey.p, 0xff, (size_t)N * 4, w.stream));
+    CK(cudaMemsetAsync(w.d_qhist.p, 0, (size_t)NLC * NQ * pb200::QBINS * 4, w.stream));
+    int* nq = ext_nq;
+    if (!nq) {
+        CK(w.d_nq.reserve((size_t)(N + 2) * 4));             // count, head, items[N]
+        nq = (int*)w.d_nq.p;
+    }
+    CK(cudaMemsetAsync(nq, 0, 8, w.stream));
     CK(cudaMemcpyAsync(w.d_offsets.p, ho, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, w.stream));
     CK(cudaMemcpyAsync(w.d_order.p, horder, (size_t)N * 4, cudaMemcpyHostToDevice, w.stream));
     CK(cudaMemcpyAsync(w.d_lenclass.p, hlc, (size_t)N * 4, cudaMemcpyHostToDevice, w.stream));
@@ -430,15 +481,22 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
             if (c->tab_on && LC_NT[lc] == 32) pa.tab_lc_mask |= 1 << lc;
         pa.grp_g = grp_g;
         pa.newton_only = (opts->algorithm == PB200_ALG_NEWTON && !d_theta_in) ? 1 : 0;
-        pa.nq_count = (int*)w.d_nq.p;
-        pa.nq_items = (int*)w.d_nq.p + 2;
+        pa.nq_count = nq;
+        pa.nq_items = nq + 2;
         pa.vcount = (int*)c->d_vcount.p;
+        pa.qkey = (int*)w.d_qkey.p;
+        pa.qhist = (int*)w.d_qhist.p;
         const int warps_per_block = 8;
         int grid = (N + warps_per_block - 1) / warps_per_block;
         grid = std::min(grid, c->sms * 8);
         pb200::prep_kernel<<<grid, warps_per_block * 32, 0, w.stream>>>(pa);
         CK(cudaGetLastError());
-        c->launches++;
+        pb200::queue_scan_kernel<<<(NLC * NQ + 127) / 128, 128, 0, w.stream>>>((int*)w.d_qhist.p, NLC * NQ);
+        CK(cudaGetLastError());
+        pb200::queue_scatter_kernel<<<std::min((N + 255) / 256, c->sms * 8), 256, 0, w.stream>>>(
+            (const int*)w.d_qkey.p, (int*)w.d_qhist.p, (int*)w.d_qitems.p, N);
+        CK(cudaGetLastError());
+        c->launches += 3;
     }
     // ---- fit kernels: one persistent launch per (length class, seasonality class) ----
     // pass 1: launch geometry and the planes workspace (one slice per resident CTA)
@@ -522,8 +580,8 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
             fa.grad_out = d_grad_out;
             fa.trace = d_trace;
             fa.trace_cap = trace_cap;
-            fa.nq_count = (int*)w.d_nq.p;
-            fa.nq_items = opts->algorithm == PB200_ALG_LBFGS_NEWTON ? (int*)w.d_nq.p + 2 : nullptr;
+            fa.nq_count = nq;
+            fa.nq_items = opts->algorithm == PB200_ALG_LBFGS_NEWTON ? nq + 2 : nullptr;
             fa.o = od;
             if (g.grouped) {
                 CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, fa, g.grid, w.stream, nullptr));
@@ -534,31 +592,9 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
         }
     }
     // ---- fbprophet's Newton retry over the series whose L-BFGS failed its line search (normally an empty queue) ----
-    if (opts->algorithm != PB200_ALG_LBFGS && !d_theta_in && L.pstride <= pb200::nw::NW_PMAX) {
-        pb200::nw::NewtonArgs na;
-        na.ds = (const long long*)d_ds;
-        na.y = d_y;
-        na.y_dtype = y_dtype;
-        na.offsets = (const long long*)w.d_offsets.p;
-        na.nq_count = (const int*)w.d_nq.p;
-        na.nq_head = (int*)w.d_nq.p + 1;
-        na.nq_items = (const int*)w.d_nq.p + 2;
-        na.params = d_params;
-        na.tchange = d_tchange;
-        na.meta_i32 = d_meta_i32;
-        na.meta_i64 = (const long long*)d_meta_i64;
-        na.meta_f64 = d_meta_f64;
-        na.smax = L.smax;
-        na.kmax = L.kmax;
-        na.pstride = L.pstride;
-        na.o = od;
-        const size_t nsm = pb200::nw::newton_smem_bytes(L.pstride);
-        CK(cudaFuncSetAttribute(pb200::nw::newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsm));
-        const int ngrid = (int)std::min<int64_t>(N, opts->algorithm == PB200_ALG_NEWTON ? (int64_t)c->sms * 2 : (int64_t)c->sms);
-        pb200::nw::newton_kernel<<<ngrid, 32 * pb200::nw::NW_WARPS, nsm, w.stream>>>(na);
-        CK(cudaGetLastError());
-        c->launches++;
-    }
+    if (!ext_nq && !d_theta_in)
+        return launch_newton(c, w.stream, opts, d_ds, d_y, y_dtype, (const int64_t*)w.d_offsets.p, n_series, nq, d_params, d_tchange,
+                             d_meta_i32, d_meta_i64, d_meta_f64);
     return PB200_OK;
 }
 
@@ -642,8 +678,11 @@ PB200_API int pb200_fit_host(pb200_ctx* c, const pb200_options* opts, const int6
     CK(c->d_mi64.reserve(N * 2 * 8));
     CK(c->d_mf64.reserve(N * 4 * 8));
     if (h_cap) CK(c->d_cap.reserve(N * 8));
+    CK(c->d_nq_all.reserve((N + 2 * 16 + 2) * 4));
+    CK(c->d_offsets_full.reserve((N + 1) * 8));
     rc = begin_fit_call(c);
     if (rc) return rc;
+    CK(cudaMemcpyAsync(c->d_offsets_full.p, h_offsets, (N + 1) * 8, cudaMemcpyHostToDevice, c->ws[0].stream));
     // series chunks with (nearly) equal rows, alternating over the two workspaces / streams: copy in, fit, copy out
     int nch = c->host_chunks;
     if (n_series < 4096 * (int64_t)nch || R < (int64_t)nch * (1 << 20)) nch = 1;
@@ -655,7 +694,7 @@ PB200_API int pb200_fit_host(pb200_ctx* c, const pb200_options* opts, const int6
     for (int k = 0; k < nch; ++k) {
         const int64_t s0 = cut[k], s1 = cut[k + 1], nk = s1 - s0;
         if (nk <= 0) continue;
-        FitWs& w = c->ws[k & 1];
+        FitWs& w = c->ws[k % NWS];
         const int64_t r0 = h_offsets[s0], rk = h_offsets[s1] - r0;
         CK(cudaMemcpyAsync((char*)c->d_ds.p + (size_t)r0 * 8, h_ds + r0, (size_t)rk * 8, cudaMemcpyHostToDevice, w.stream));
         CK(cudaMemcpyAsync((char*)c->d_y.p + (size_t)r0 * ye, (const char*)h_y + (size_t)r0 * ye, (size_t)rk * ye,
@@ -671,8 +710,33 @@ PB200_API int pb200_fit_host(pb200_ctx* c, const pb200_options* opts, const int6
                       floor, cap_multiplier, dcap, (double*)c->d_params.p + (size_t)s0 * L.pstride,
                       (double*)c->d_tchange.p + (size_t)s0 * L.smax, (int32_t*)c->d_mi32.p + (size_t)s0 * 8,
                       (int64_t*)c->d_mi64.p + (size_t)s0 * 2, (double*)c->d_mf64.p + (size_t)s0 * 4, nullptr, nullptr, nullptr, 0,
-                      n_series);
+                      n_series, (int*)c->d_nq_all.p + s0 + 2 * k);
         if (rc) return rc;
+    }
+    // Newton retries, normally none: the per-chunk queue lengths are read back once every chunk's fit is done
+    if (opts->algorithm != PB200_ALG_LBFGS) {
+        for (FitWs& w : c->ws) CK(cudaStreamSynchronize(w.stream));
+        for (int k = 0; k < nch; ++k) {
+            const int64_t s0 = cut[k], nk = cut[k + 1] - s0;
+            if (nk <= 0) continue;
+            int* nq = (int*)c->d_nq_all.p + s0 + 2 * k;
+            int cnt = 0;
+            CK(cudaMemcpy(&cnt, nq, 4, cudaMemcpyDeviceToHost));
+            if (cnt <= 0) continue;
+            // chunk-local series indices, the call's un-rebased offsets: ds / y are passed whole
+            rc = launch_newton(c, c->ws[k % NWS].stream, opts, (const int64_t*)c->d_ds.p, c->d_y.p, y_dtype,
+                               (const int64_t*)c->d_offsets_full.p + s0, nk, nq, (double*)c->d_params.p + (size_t)s0 * L.pstride,
+                               (double*)c->d_tchange.p + (size_t)s0 * L.smax, (int32_t*)c->d_mi32.p + (size_t)s0 * 8,
+                               (int64_t*)c->d_mi64.p + (size_t)s0 * 2, (double*)c->d_mf64.p + (size_t)s0 * 4);
+            if (rc) return rc;
+        }
+    }
+    // results back, chunk by chunk, only after EVERY chunk is enqueued: a copy into pageable caller memory blocks the
+    // host until its stream gets there, and issued inside the loop above it serialised the chunks (r2h: e2e / value 0.71)
+    for (int k = 0; k < nch; ++k) {
+        const int64_t s0 = cut[k], nk = cut[k + 1] - s0;
+        if (nk <= 0) continue;
+        FitWs& w = c->ws[k % NWS];
         const size_t n0 = (size_t)s0, nn = (size_t)nk;
         CK(cudaMemcpyAsync(h_params + n0 * L.pstride, (double*)c->d_params.p + n0 * L.pstride, nn * L.pstride * 8, cudaMemcpyDeviceToHost, w.stream));
         CK(cudaMemcpyAsync(h_tchange + n0 * L.smax, (double*)c->d_tchange.p + n0 * L.smax, nn * L.smax * 8, cudaMemcpyDeviceToHost, w.stream));

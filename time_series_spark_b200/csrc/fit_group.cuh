@@ -43,18 +43,23 @@ struct GState {
     LSState ls;
     double cap_s, sigma, hstep, zmax;
     int T, S, ncp, chunk, tabP, tabPL, series, state, exprec, st0, i1max, pad_;
-    double kc[GSEG], mc[GSEG], rho[GSEG], tc[GSEG], qs[GSEG], bndU[GSEG], bndV[GSEG];
+    double kc[GSEG], mc[GSEG], tc[GSEG], qs[GSEG], bndU[GSEG], bndV[GSEG];
     int bidx[GSEG];
     alignas(16) double bcoef[16];
-    double hrho[8], halpha[8];
+    double hrho[8];
     alignas(16) double rotw[2];          // (sin, cos) of one grid step's advance of the weekly angle
     alignas(16) double rotd[2];          // ... of the daily angle
     alignas(16) double stab[GPT];        // s_p: daily part of X beta at table phase p
     alignas(16) double rtab[GPT];        // R_p: residual bins; stab / rtab double as the reduction scratch
-    int j0l[G];                          // trend segment of the point before each lane's chunk
-    double2 wph[G];                      // weekly (sin, cos) at each lane's first point
-    double2 dph[G];                      // daily (sin, cos) at each lane's first table phase
     alignas(16) double vec[6][GPPAD];    // x g p x_trial g_trial p_prev (roles in ls.ix ...)
+};
+
+// per-lane constants of a lane's chunk of ITS series, kept in registers between evaluations (g_fetch leaves them in the
+// table storage, which is dead outside a pass)
+struct LanePhase {
+    double2 wph;        // weekly (sin, cos) at the lane's first point
+    double2 dph;        // daily (sin, cos) at the lane's first table phase
+    int j0;             // trend segment of the point before the lane's chunk
 };
 
 template <int G>
@@ -193,7 +198,6 @@ __device__ __noinline__ void g_eval_setup(GState<G>& s, const double* xv, const 
                 s.kc[j] = kcl[u];
                 s.mc[j] = mcl[u];
                 s.qs[j] = exp_fastpath(-(kcl[u] * h));
-                if (j < S) s.rho[j] = ra[u];
                 // the exponent k_j (t - m_j) is piecewise linear in t: its extremes sit at the segment ends
                 const double tl = j == 0 ? -h : s.tc[j - 1];
                 const double tr = j == S ? 1.0 : tcl[u];
@@ -254,14 +258,19 @@ struct GPoint {
             tm = t;
             g = fma(kcj, t, mcj);
         }
+        // multiplicative mode: the table entry already holds 1 + (daily part), so dot = 1 + X beta
         double opm, yhat;
-        if constexpr (MULT) { opm = 1.0 + dot; yhat = g * opm; }
+        if constexpr (MULT) { opm = dot; yhat = g * opm; }
         else { opm = 1.0; yhat = g + dot; }
         r = valid ? y - yhat : 0.0;
         cb = MULT ? r * g : r;
-        const double qv = MULT ? r * opm : r;
-        if constexpr (LOGI) dz = qv * g * (1.0 - sig);
-        else dz = qv;
+        if constexpr (LOGI) {
+            // d/dz of the trend term: r opm g (1 - sig) = (cb opm)(1 - sig) in multiplicative mode
+            const double qg = MULT ? cb * opm : r * g;
+            dz = qg * (1.0 - sig);
+        } else {
+            dz = MULT ? r * opm : r;
+        }
     }
 };
 
@@ -270,11 +279,11 @@ struct GPoint {
 // ---------------------------------------------------------------------------------------
 template <int G, bool LOGI, bool MULT, int U>
 __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, const bool active, const int gl, const int lane,
-                                          const unsigned gm) {
+                                          const unsigned gm, const LanePhase lp) {
     static_assert(U == 2 || U == 4, "points per lane per step");
     const int P = active ? s.tabP : GPT, PL = active ? s.tabPL : 0;     // (an idle group's lanes only keep step)
     const double2 rct = *reinterpret_cast<const double2*>(s.rotd);
-    const double2 w0 = s.dph[gl];
+    const double2 w0 = lp.dph;
     // ---- seasonal table of this evaluation; residual bins cleared ----
     if (active) {
         double2 w = w0;
@@ -291,7 +300,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
                     d0 = fma(b.x, X[k], d0);
                     d1 = fma(b.y, X[k + 1], d1);
                 }
-                s.stab[p] = d0 + d1;
+                s.stab[p] = (MULT ? 1.0 : 0.0) + (d0 + d1);       // multiplicative: 1 + seasonal sum, see GPoint::run
                 s.rtab[p] = 0.0;
             }
             const double sn = fma(w.x, rct.y, w.y * rct.x);
@@ -304,7 +313,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     const int i0 = active ? (gl * chunk < T ? gl * chunk : T) : 0;
     const int i1 = active ? (i0 + chunk < T ? i0 + chunk : T) : 0;
     const int npts = i1 - i0;
-    int j = active ? s.j0l[gl] : 0;                    // trend segment of the point before the chunk (set by g_fetch)
+    int j = active ? lp.j0 : 0;                        // trend segment of the point before the chunk
     const int j0 = j;
     double gacc[GK];
 #pragma unroll
@@ -342,7 +351,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     cp_async_commit();
     const double2* gnext = gsrc + G * (U / 2);
     int pb = P > 0 ? i0 % P : 0;
-    double2 ws = s.wph[gl];
+    double2 ws = lp.wph;
     const double2 rcw = *reinterpret_cast<const double2*>(s.rotw);
     // weekly coefficients in registers (loop invariant; as shared-memory operands they were re-read every step because
     // the bin stores may alias them as far as the compiler can tell)
@@ -572,13 +581,16 @@ __device__ __noinline__ int g_eval_finalize(GState<G>& s, const double* xv, doub
             PV[u + 1] = j <= S ? s.bndV[j] : totV;
             kcl[u] = j <= S ? s.kc[j] : 1.0;
             mcl[u] = j <= S ? s.mc[j] : 0.0;
-            rhl[u] = j < S ? s.rho[j] : 1.0;
+            rhl[u] = 1.0;                                   // rho_j = k_j / k_{j+1}: recomputed below (same expression as g_eval_setup)
             tcl[u] = j < S ? s.tc[j] : 0.0;
             Gkc[u] = j <= S ? scale * (PU[u + 1] - PU[u]) : 0.0;
             Gmc[u] = j <= S ? scale * (-kcl[u]) * (PV[u + 1] - PV[u]) : 0.0;
         }
         kcl[NS] = __shfl_down_sync(gm, kcl[0], 1, G);
         if (jb + NS > S) kcl[NS] = 1.0;
+#pragma unroll
+        for (int u = 0; u < NS; ++u)
+            if (jb + u < S) rhl[u] = div_const(kcl[u], kcl[u + 1], rcp_any(kcl[u + 1]));
         // abar_S = Gmc_S, abar_j = Gmc_j + rho_j abar_{j+1}: reverse scan of the affine maps x -> a x + b
         // (a, b) = (rho_j, Gmc_j) for j < S, (0, Gmc_S) at j = S, identity above
         double ma[NS], mb[NS], A = 1.0, B = 0.0;
@@ -1034,10 +1046,10 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
         const double tw = (1e-9 * (double)(d0 + (long long)i0 * step)) / 86400.0;
         double s_, c_;
         sincos(TWO_PI_FL * tw / 7.0, &s_, &c_);
-        s.wph[gl] = make_double2(s_, c_);
+        reinterpret_cast<double2*>(s.stab)[gl] = make_double2(s_, c_);           // LanePhase hand-over, see the kernel
         const double td = (1e-9 * (double)(d0 + (long long)(gl * PL) * step)) / 86400.0;
         sincos(TWO_PI_FL * td / 1.0, &s_, &c_);
-        s.dph[gl] = make_double2(s_, c_);
+        reinterpret_cast<double2*>(s.stab)[G + gl] = make_double2(s_, c_);
     }
     // ---- changepoints (Prophet.set_changepoints) and segment boundaries ----
 #pragma unroll 1
@@ -1070,7 +1082,7 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
         int j0 = 0;
 #pragma unroll 1
         for (int q = 0; q < S; ++q) j0 += s.bidx[q] < i0 ? 1 : 0;
-        s.j0l[gl] = j0;
+        reinterpret_cast<int*>(s.stab)[4 * GPT - G + gl] = j0;      // (the last G ints of the stab / rtab storage)
     }
     // ---- initial point: Prophet.{linear,logistic}_growth_init + stan_init ----
     {
@@ -1153,8 +1165,9 @@ __device__ __noinline__ void g_write_record(GState<G>& s, const FitArgs& a, cons
 // the kernel: one warp per CTA, 32 / G series in flight per warp, persistent over the class's work queue
 // ---------------------------------------------------------------------------------------
 template <int G, bool LOGI, bool MULT>
-__global__ void __launch_bounds__(32, G == 8 ? 8 : 16) fit_group_kernel(const FitArgs a) {
+__global__ void __launch_bounds__(32, G == 8 ? 9 : 16) fit_group_kernel(const FitArgs a) {
     static_assert(G == 8 || G == 16 || G == 32, "lanes per series");
+    static_assert(4 * G * 8 + G * 4 <= 2 * GPT * 8, "LanePhase hand-over through the table storage");
     constexpr int NSER = 32 / G;
     const int lane = threadIdx.x & 31, gi = lane / G, gl = lane % G;
     const unsigned gm = G == 32 ? FULL : (((1u << G) - 1u) << (gi * G));
@@ -1171,10 +1184,16 @@ __global__ void __launch_bounds__(32, G == 8 ? 8 : 16) fit_group_kernel(const Fi
     const double init_alpha = a.o.init_alpha;
     const int trace_cap = a.trace_cap;
     bool exhausted = false;
+    LanePhase lp;
+    lp.wph = lp.dph = make_double2(0.0, 1.0);
+    lp.j0 = 0;
     for (;;) {
         // ---- idle groups take the next series of the queue ----
         if (s.state == ST_IDLE && !exhausted) {
             if (g_fetch<G, LOGI>(s, a, plane, gl, gm)) {
+                lp.wph = reinterpret_cast<const double2*>(s.stab)[gl];
+                lp.dph = reinterpret_cast<const double2*>(s.stab)[G + gl];
+                lp.j0 = reinterpret_cast<const int*>(s.stab)[4 * GPT - G + gl];
                 int st = ST_FIRST;
                 if (a.theta_in) st = ST_OBJ;
                 else if (s.st0 == PB200_ST_CONST_LINEAR) {
@@ -1204,7 +1223,7 @@ __global__ void __launch_bounds__(32, G == 8 ? 8 : 16) fit_group_kernel(const Fi
             if (gl == 0) s.ls.nevals += 1;
         }
         __syncwarp();
-        g_point_pass<G, LOGI, MULT, grp_u(G)>(s, plane, active, gl, lane, gm);
+        g_point_pass<G, LOGI, MULT, grp_u(G)>(s, plane, active, gl, lane, gm, lp);
         __syncwarp();
         int err = 0;
         if (active) err = g_eval_finalize<G, LOGI>(s, s.vec[ixv], s.vec[igv], gl, gm, tau, rtau, inv_seas2, first ? &s.ls.fk : &s.ls.ft);
