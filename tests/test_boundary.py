@@ -248,3 +248,20 @@ def test_null_group_key_is_refused():
                     "ds": pa.array([0, 1], pa.int64()).cast(pa.timestamp("ns")), "y": pa.array([1, 2], pa.int32())})
     with pytest.raises(ValueError, match="null"):
         pack_groups(tbl, pin=False)
+
+
+def test_fbprophet_pickle_importer_says_why_it_cannot_run_here():
+    """The reference's models are pickled Prophet objects; importing them needs fbprophet itself (absent here)."""
+    from time_series_spark_b200 import model_record
+    try:
+        import fbprophet  # noqa: F401
+        pytest.skip("fbprophet is importable: the importer can actually run")
+    except ImportError:
+        pass
+    try:
+        import prophet  # noqa: F401
+        pytest.skip("prophet is importable")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError, match="fbprophet"):
+        model_record.from_fbprophet_pickle([b"not a pickle"])

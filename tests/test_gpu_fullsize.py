@@ -91,21 +91,21 @@ def test_config4_full_size_ragged(gpu_ctx):
 
 
 def test_chunked_host_fit_equals_single_pass(gpu_ctx):
-    """pb200_fit_host cuts big batches into series chunks over two streams (copy / compute overlap); a series' result
-    must not depend on the chunking."""
+    """pb200_fit_host can cut a big batch into series chunks over several streams (PB200_HOST_CHUNKS; copy / compute
+    overlap -- off by default because it measured slower); a series' result must not depend on the chunking."""
     import os
     b = synth.config4(n=40_000)
     opts = batched.make_options()
-    fb = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)            # 4 chunks of ~10k series
-    os.environ["PB200_HOST_CHUNKS"] = "1"
+    f1 = batched.fit_batch_host(gpu_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)            # one pass
+    os.environ["PB200_HOST_CHUNKS"] = "4"
     try:
-        one = L.Context(0)
+        four = L.Context(0)
     finally:
         del os.environ["PB200_HOST_CHUNKS"]
     try:
-        f1 = batched.fit_batch_host(one, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+        fb = batched.fit_batch_host(four, opts, b.ds, b.y, b.offsets, 0.0, 1.1)           # 4 chunks of ~10k series
+        assert four.last_fit_variant_counts().sum() == b.n      # counted over all chunks of the call
     finally:
-        one.close()
+        four.close()
     assert np.array_equal(fb.params, f1.params) and np.array_equal(fb.meta_i32, f1.meta_i32)
     assert np.array_equal(fb.meta_f64, f1.meta_f64, equal_nan=True) and np.array_equal(fb.tchange, f1.tchange)
-    assert gpu_ctx.last_fit_variant_counts().sum() == b.n       # counted over all chunks of the call

@@ -98,3 +98,14 @@ def test_gpu_pack_matches_host_pack():
     # rows with equal (series, dim, ds) may be ordered differently by the two stable sorts only if the input
     # order differs, which it does not: y must match exactly as well
     assert np.array_equal(h.y, g.y.cpu().numpy())
+
+
+def test_make_future_device_matches_host(gpu_ctx):
+    """pb200_make_future_device = Prophet.make_future_dataframe(include_history=False) for a fixed-width frequency:
+    last + (1..periods) * freq, the grid batched.make_future builds on the host (and pandas date_range in test_boundary)."""
+    import torch
+    from time_series_spark_b200 import batched
+    last = np.array([0, 1_546_300_800 * 10**9, 1_615_851_900 * 10**9, -5 * 10**9], np.int64)
+    for periods, freq in ((40, 15 * 60 * 10**9), (1, 7 * 86400 * 10**9), (672, 15 * 60 * 10**9)):
+        got = batched.make_future_device(gpu_ctx, torch.from_numpy(last).cuda(), periods, freq).cpu().numpy()
+        assert np.array_equal(got, batched.make_future(last, periods, freq))

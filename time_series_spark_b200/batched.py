@@ -194,6 +194,20 @@ def make_future(last_ds_ns: np.ndarray, periods: int, freq_ns: int) -> np.ndarra
     return last[:, None] + np.int64(freq_ns) * np.arange(1, periods + 1, dtype=np.int64)[None, :]
 
 
+def make_future_device(ctx: L.Context, last_ds_ns, periods: int, freq_ns: int):
+    """pb200_make_future_device: the same grid built on the GPU from a CUDA int64 tensor of last history timestamps
+    (for callers that keep the scorer's inputs resident)."""
+    import torch
+    n = int(last_ds_ns.shape[0])
+    out = torch.empty((n, periods), dtype=torch.int64, device=last_ds_ns.device)
+    if n and periods:
+        torch.cuda.current_stream(last_ds_ns.device).synchronize()
+        rc = L.load().pb200_make_future_device(ctx.handle, last_ds_ns.data_ptr(), n, int(periods), int(freq_ns), out.data_ptr())
+        L.check(rc, "pb200_make_future_device")
+        ctx.synchronize()
+    return out
+
+
 def predict_batch_host(ctx: L.Context, opts: L.Options, fitted: FittedBatch, future_ds: np.ndarray,
                        floor: np.ndarray, cap: np.ndarray, seed: int = 0, intervals: bool = True) -> ForecastBatch:
     """pb200_predict_host.  ``floor`` / ``cap`` per model as the scorer reads them back from

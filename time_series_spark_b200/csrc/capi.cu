@@ -119,7 +119,9 @@ struct pb200_ctx {
     DevBuf d_nq_all, d_offsets_full;   // pb200_fit_host: per-chunk Newton retry queues, the call's offsets on the device
     int grp_min = 16384;   // PB200_GROUP_MIN: smallest batch the grouped kernel takes (below it its 4-series warps leave a longer
                            // straggler tail than one warp per series: r2e, 6250 series: 105 vs 80 ms; 50k: 419 vs 470 ms)
-    int host_chunks = 4;   // PB200_HOST_CHUNKS: series chunks of pb200_fit_host (1 = no overlap)
+    int host_chunks = 1;   // PB200_HOST_CHUNKS: series chunks of pb200_fit_host.  Default 1 (one pass): measured on 50k x 1440
+                           // (r2j / r2k) 1 / 2 / 4 / 8 chunks = 397 / 407 / 440 / 500 ms -- the 865 MB copy is only ~25 ms at
+                           // PCIe 5 speed, and every chunk pays its own straggler drain, which costs more than it hides
 };
 
 namespace {
@@ -265,7 +267,7 @@ PB200_API pb200_ctx* pb200_create(int device) {
         return nullptr;
     }
     c->stream = c->ws[0].stream;
-    c->host_chunks = std::max(1, std::min(16, env_int("PB200_HOST_CHUNKS", NWS)));
+    c->host_chunks = std::max(1, std::min(16, env_int("PB200_HOST_CHUNKS", 1)));
     c->lc_max[0] = env_int("PB200_LC0_MAX", 1 << 30);   // warp-per-series for every length
     c->lc_max[1] = env_int("PB200_LC1_MAX", 1 << 30);
     c->lc_max[2] = 1 << 30;

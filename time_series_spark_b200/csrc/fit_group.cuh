@@ -54,10 +54,11 @@ struct GState {
     alignas(16) double vec[6][GPPAD];    // x g p x_trial g_trial p_prev (roles in ls.ix ...)
 };
 
-// per-lane constants of a lane's chunk of ITS series, kept in registers between evaluations (g_fetch leaves them in the
-// table storage, which is dead outside a pass)
+// per-lane constants of a lane's chunk of ITS series, kept in registers between evaluations (g_fetch leaves them in
+// vec[1..5], which nothing reads before the first evaluation has written them)
 struct LanePhase {
-    double2 wph;        // weekly (sin, cos) at the lane's first point
+    double2 wph;        // weekly (sin, cos) two points before the lane's first point
+    double2 wend;       // weekly (sin, cos) at the lane's second last point (padded to whole two-point steps)
     double2 dph;        // daily (sin, cos) at the lane's first table phase
     int j0;             // trend segment of the point before the lane's chunk
 };
@@ -231,24 +232,10 @@ __device__ __forceinline__ void day_features(const double2 w, double* X) { harmo
 // one point: everything between the loads and the accumulations
 template <bool LOGI, bool MULT>
 struct GPoint {
-    double X[GKW];
     double r, cb, dz, tm;
-    __device__ __forceinline__ void run(const double y, const double t, const double sp, double2& ws, const double2 rcw,
-                                        const double (&bcoef)[GKW], const double e, const double kcj, const double mcj,
-                                        const double cap, const bool valid) {
-        harmonics<3>(ws, X);
-        {
-            const double sn = fma(ws.x, rcw.y, ws.y * rcw.x);
-            const double cn = fma(ws.y, rcw.y, -(ws.x * rcw.x));
-            ws = make_double2(sn, cn);
-        }
-        double dot = sp, d1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < GKW; k += 2) {
-            dot = fma(bcoef[k], X[k], dot);
-            d1 = fma(bcoef[k + 1], X[k + 1], d1);
-        }
-        dot += d1;
+    // dot: the seasonal term X beta of the point (table entry + weekly part; 1 + X beta in multiplicative mode)
+    __device__ __forceinline__ void run(const double y, const double t, const double dot, const double e, const double kcj,
+                                        const double mcj, const double cap, const bool valid) {
         double g, sig = 0.0;
         if constexpr (LOGI) {
             tm = t - mcj;
@@ -351,13 +338,40 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     cp_async_commit();
     const double2* gnext = gsrc + G * (U / 2);
     int pb = P > 0 ? i0 % P : 0;
-    double2 ws = lp.wph;
-    const double2 rcw = *reinterpret_cast<const double2*>(s.rotw);
-    // weekly coefficients in registers (loop invariant; as shared-memory operands they were re-read every step because
-    // the bin stores may alias them as far as the compiler can tell)
-    double bw[GKW];
+    // The weekly part of the seasonal term and of the beta gradient WITHOUT the six weekly features per point.  Every
+    // harmonic h of the weekly angle obeys the three-term recurrence y(i + 1) = c_h y(i) - y(i - 1), c_h = 2 cos(h delta),
+    // for its sine, its cosine and therefore for u_h(i) = beta_sh sin + beta_ch cos:
+    //   * the seasonal term: u_h advanced IN PLACE on its values at the previous two points (one DFMA per harmonic and
+    //     point; after a two-point step the pair again holds the last two points in order);
+    //   * the gradient sum_i c_i y(i): Clenshaw's recurrence on the reversed sequence, B_i = c_h B_{i-1} + c_i - B_{i-2}
+    //     (two operations per harmonic and point, serving sine AND cosine), closed after the lane's last point with
+    //     sum = y(n-1) (B_{n-1} - c_h B_{n-2}) + y(n-2) B_{n-2}.
+    // 12 FP64 operations per point instead of 19 (r2m: features by recurrence 6 + dot 7 + gradient 6), 25 (r2b: rotation).
+    // Rounding: recurrences grow errors like n eps / sin(h delta), delta = 2 pi / 672: ~1e-12 of the term over a
+    // 180-point chunk (measured against 40-digit arithmetic: 6e-13 for h = 1) -- inside the 1e-10 objective and 1e-8
+    // gradient tolerances, and every evaluation restarts from the lane's exact start / end phases.
+    static_assert(U == 2, "the in-place three-term recurrences are written for two points per step");
+    constexpr int NH = GKW / 2;
+    double uw[NH][2], Bw[NH][2], cw[NH];
+    const int nown = active ? 2 * ((npts + 1) >> 1) : 0;       // this lane's own points (padded to whole steps)
+    {
+        const double2 rcw = *reinterpret_cast<const double2*>(s.rotw);
+        double Xr[GKW], X0[GKW], X1[GKW];
+        harmonics<3>(rcw, Xr);                              // cos(h delta) at the odd positions
+        double2 w = lp.wph;                                 // weekly angle at point i0 - 2
+        harmonics<3>(w, X0);
+        w = make_double2(fma(w.x, rcw.y, w.y * rcw.x), fma(w.y, rcw.y, -(w.x * rcw.x)));
+        harmonics<3>(w, X1);                                // ... and at i0 - 1
 #pragma unroll
-    for (int k = 0; k < GKW; ++k) bw[k] = s.bcoef[k];
+        for (int hh = 0; hh < NH; ++hh) {
+            cw[hh] = 2.0 * Xr[2 * hh + 1];
+            const double bs = s.bcoef[2 * hh], bc = s.bcoef[2 * hh + 1];
+            uw[hh][0] = fma(bs, X0[2 * hh], bc * X0[2 * hh + 1]);
+            uw[hh][1] = fma(bs, X1[2 * hh], bc * X1[2 * hh + 1]);
+            Bw[hh][0] = 0.0;
+            Bw[hh][1] = 0.0;
+        }
+    }
     double tt[U];                                       // t of the step's points, advanced by U h per step
 #pragma unroll
     for (int u = 0; u < U; ++u) tt[u] = (double)(i0 + u) * h;
@@ -432,15 +446,23 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         }
         GPoint<LOGI, MULT> pt[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) pt[u].run(yv[u], tt[u], sp[u], ws, rcw, bw, ee[u], kcu[u], mcu[u], cap, val[u]);
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) uw[hh][u] = fma(cw[hh], uw[hh][u ^ 1], -uw[hh][u]);
+            const double dot = sp[u] + ((uw[0][u] + uw[1][u]) + uw[2][u]);
+            pt[u].run(yv[u], tt[u], dot, ee[u], kcu[u], mcu[u], cap, val[u]);
+            // (beyond the lane's own points c_i = 0 and B must stand still: only the checked tail steps can get there)
+            if (!CHECK || n + u < nown) {
+#pragma unroll
+                for (int hh = 0; hh < NH; ++hh) Bw[hh][u] = fma(cw[hh], Bw[hh][u ^ 1], pt[u].cb) - Bw[hh][u];
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) tt[u] += hU;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             ss = fma(pt[u].r, pt[u].r, ss);
             if (val[u]) s.rtab[pu[u]] = Rv[u] + pt[u].cb;      // R_p += c_i (bins of a step are pairwise distinct)
-#pragma unroll
-            for (int k = 0; k < GKW; ++k) gacc[k] = fma(pt[u].cb, pt[u].X[k], gacc[k]);
         }
         double preU[U + 1], preV[U + 1];
         preU[0] = locU;
@@ -469,6 +491,21 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     for (; m < nfull; ++m) step(m, std::false_type{});
 #pragma unroll 1
     for (; m < nstep; ++m) step(m, std::true_type{});
+    {   // weekly beta gradient: close the Clenshaw sums with the features of the lane's last two (padded) points
+        const double2 rcw = *reinterpret_cast<const double2*>(s.rotw);
+        double Y2[GKW], Y1[GKW];
+        double2 w = lp.wend;                                // weekly angle at point i0 + nown - 2
+        harmonics<3>(w, Y2);
+        w = make_double2(fma(w.x, rcw.y, w.y * rcw.x), fma(w.y, rcw.y, -(w.x * rcw.x)));
+        harmonics<3>(w, Y1);                                // ... at i0 + nown - 1
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+            const double B1 = Bw[hh][1], B2 = Bw[hh][0];    // B at the last and the second last point
+            const double D = fma(-cw[hh], B2, B1);
+            gacc[2 * hh] = fma(Y1[2 * hh], D, Y2[2 * hh] * B2);
+            gacc[2 * hh + 1] = fma(Y1[2 * hh + 1], D, Y2[2 * hh + 1] * B2);
+        }
+    }
     // ---- table features' beta gradient from the residual bins ----
     if (active) {
         double2 w = w0;
@@ -1043,13 +1080,17 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
     {
         const long long d0 = a.ds[off];
         const int i0 = gl * chunk;
-        const double tw = (1e-9 * (double)(d0 + (long long)i0 * step)) / 86400.0;
+        const double tw = (1e-9 * (double)(d0 + (long long)(i0 - 2) * step)) / 86400.0;     // two points before the chunk
         double s_, c_;
         sincos(TWO_PI_FL * tw / 7.0, &s_, &c_);
-        reinterpret_cast<double2*>(s.stab)[gl] = make_double2(s_, c_);           // LanePhase hand-over, see the kernel
+        reinterpret_cast<double2*>(&s.vec[1][0])[gl] = make_double2(s_, c_);    // LanePhase hand-over through the vectors that are dead until the first evaluation, see the kernel
         const double td = (1e-9 * (double)(d0 + (long long)(gl * PL) * step)) / 86400.0;
         sincos(TWO_PI_FL * td / 1.0, &s_, &c_);
-        reinterpret_cast<double2*>(s.stab)[G + gl] = make_double2(s_, c_);
+        reinterpret_cast<double2*>(&s.vec[1][0])[G + gl] = make_double2(s_, c_);
+        const int i1 = i0 + chunk < T ? i0 + chunk : T, np_ = i1 > i0 ? i1 - i0 : 0;
+        const double te = (1e-9 * (double)(d0 + (long long)(i0 + 2 * ((np_ + 1) >> 1) - 2) * step)) / 86400.0;
+        sincos(TWO_PI_FL * te / 7.0, &s_, &c_);
+        reinterpret_cast<double2*>(&s.vec[1][0])[2 * G + gl] = make_double2(s_, c_);
     }
     // ---- changepoints (Prophet.set_changepoints) and segment boundaries ----
 #pragma unroll 1
@@ -1082,7 +1123,7 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
         int j0 = 0;
 #pragma unroll 1
         for (int q = 0; q < S; ++q) j0 += s.bidx[q] < i0 ? 1 : 0;
-        reinterpret_cast<int*>(s.stab)[4 * GPT - G + gl] = j0;      // (the last G ints of the stab / rtab storage)
+        reinterpret_cast<int*>(&s.vec[1][0] + 6 * G)[gl] = j0;
     }
     // ---- initial point: Prophet.{linear,logistic}_growth_init + stan_init ----
     {
@@ -1165,9 +1206,15 @@ __device__ __noinline__ void g_write_record(GState<G>& s, const FitArgs& a, cons
 // the kernel: one warp per CTA, 32 / G series in flight per warp, persistent over the class's work queue
 // ---------------------------------------------------------------------------------------
 template <int G, bool LOGI, bool MULT>
-__global__ void __launch_bounds__(32, G == 8 ? 9 : 16) fit_group_kernel(const FitArgs a) {
+#ifndef PB200_GRP_BLOCKS
+// resident one-warp CTAs per SM the G = 8 register budget is set for.  8 -> 215 registers; 9 -> 168 registers with spills in
+// g_post_accept: 405 vs 376 ms per 50k-series step on the same box (r2l), whether 8 or 9 CTAs are actually resident (the
+// shared-memory footprint allows 9 either way: occupancy is not what limits this kernel)
+#define PB200_GRP_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(32, G == 8 ? PB200_GRP_BLOCKS : 16) fit_group_kernel(const FitArgs a) {
     static_assert(G == 8 || G == 16 || G == 32, "lanes per series");
-    static_assert(4 * G * 8 + G * 4 <= 2 * GPT * 8, "LanePhase hand-over through the table storage");
+    static_assert(6 * G * 8 + G * 4 <= 5 * GPPAD * 8, "LanePhase hand-over through vec[1..5]");
     constexpr int NSER = 32 / G;
     const int lane = threadIdx.x & 31, gi = lane / G, gl = lane % G;
     const unsigned gm = G == 32 ? FULL : (((1u << G) - 1u) << (gi * G));
@@ -1185,15 +1232,16 @@ __global__ void __launch_bounds__(32, G == 8 ? 9 : 16) fit_group_kernel(const Fi
     const int trace_cap = a.trace_cap;
     bool exhausted = false;
     LanePhase lp;
-    lp.wph = lp.dph = make_double2(0.0, 1.0);
+    lp.wph = lp.dph = lp.wend = make_double2(0.0, 1.0);
     lp.j0 = 0;
     for (;;) {
         // ---- idle groups take the next series of the queue ----
         if (s.state == ST_IDLE && !exhausted) {
             if (g_fetch<G, LOGI>(s, a, plane, gl, gm)) {
-                lp.wph = reinterpret_cast<const double2*>(s.stab)[gl];
-                lp.dph = reinterpret_cast<const double2*>(s.stab)[G + gl];
-                lp.j0 = reinterpret_cast<const int*>(s.stab)[4 * GPT - G + gl];
+                lp.wph = reinterpret_cast<const double2*>(&s.vec[1][0])[gl];
+                lp.dph = reinterpret_cast<const double2*>(&s.vec[1][0])[G + gl];
+                lp.wend = reinterpret_cast<const double2*>(&s.vec[1][0])[2 * G + gl];
+                lp.j0 = reinterpret_cast<const int*>(&s.vec[1][0] + 6 * G)[gl];
                 int st = ST_FIRST;
                 if (a.theta_in) st = ST_OBJ;
                 else if (s.st0 == PB200_ST_CONST_LINEAR) {

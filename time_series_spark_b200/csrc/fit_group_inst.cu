@@ -1,5 +1,7 @@
 // Instantiations of the grouped-lanes fit kernel (fit_group.cuh): G in {8, 16, 32} lanes per series x growth x
 // seasonality mode, for the weekly + daily day-table class.
+#include <cstdlib>
+
 #include "fit_group.cuh"
 #include "launch.h"
 
@@ -8,7 +10,9 @@ namespace pb200 {
 template <int G, bool LOGI, bool MULT>
 static cudaError_t launch_group_one(const FitArgs& a, int grid, cudaStream_t st, int* occ) {
     auto kern = grp::fit_group_kernel<G, LOGI, MULT>;
-    const size_t smem = grp::group_smem_bytes<G>();
+    // PB200_GRP_PAD (A/B runs only): extra dynamic shared memory per CTA, i.e. fewer resident warps per SM
+    static const size_t pad = getenv("PB200_GRP_PAD") ? (size_t)atoi(getenv("PB200_GRP_PAD")) : 0;
+    const size_t smem = grp::group_smem_bytes<G>() + pad;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, 32, smem);

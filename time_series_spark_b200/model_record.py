@@ -91,3 +91,82 @@ def decode(col) -> tuple:
     info = {"logistic": bool(flags & FLAG_LOGISTIC), "multiplicative": bool(flags & FLAG_MULT),
             "yearly": int(sw[0]), "weekly": int(sw[1]), "daily": int(sw[2]), "n_changepoints": int(sw[3])}
     return fb, np.ascontiguousarray(rec["last_ds"]), info
+
+
+def from_fbprophet_pickle(blobs, floor=None, cap=None):
+    """Models written by the REFERENCE (``pickle.dumps(Prophet object)``, src/jobs/prophet_modeler.py:72-73) ->
+    (FittedBatch, last_ds_ns, options dict), so that genuine fbprophet fits can be scored on the GPU path -- and
+    compared with this repo's fits of the same input, the strongest parity check there is (BASELINE.md
+    section 2).
+
+    Unpickling a Prophet object needs ``fbprophet`` (0.5, the reference's pin) or ``prophet`` importable; neither
+    exists in this image (no network), so this function has NOT been exercised against a real pickle: it follows
+    fbprophet 0.5's attribute names as recalled -- ``params`` {'k','m','delta','sigma_obs','beta'} (1 x n arrays),
+    ``changepoints_t``, ``start``, ``t_scale``, ``y_scale``, ``seasonalities`` (OrderedDict name -> period /
+    fourier_order / mode), ``growth``, ``seasonality_mode``, ``history_dates`` -- and raises ImportError with the
+    reason when the class cannot be imported.  Only the default seasonalities (yearly 10, weekly 3, daily 4) map
+    onto the compiled kernels; anything else is refused."""
+    import pickle
+    try:
+        try:
+            import fbprophet  # noqa: F401
+        except ImportError:
+            import prophet  # noqa: F401
+    except ImportError as exc:
+        raise ImportError("reading the reference's model pickles needs fbprophet (or prophet) importable: "
+                          "pickle.loads re-creates a fbprophet.forecaster.Prophet object") from exc
+    models = [pickle.loads(b) for b in blobs]
+    n = len(models)
+    if n == 0:
+        raise ValueError("no models")
+    m0 = models[0]
+    logistic = m0.growth == "logistic"
+    mult = getattr(m0, "seasonality_mode", "additive") == "multiplicative"
+    orders = {"yearly": 10, "weekly": 3, "daily": 4}
+    smax = max(1, max(len(np.atleast_1d(m.changepoints_t)) for m in models))
+    sw = {k: 0 for k in orders}
+    for m in models:
+        for name, spec in m.seasonalities.items():
+            if name not in orders or int(spec["fourier_order"]) != orders[name]:
+                raise ValueError(f"seasonality {name!r} (order {spec.get('fourier_order')}) has no compiled kernel")
+            sw[name] = 1
+    kmax = sum(2 * orders[k] for k in orders if sw[k]) or 1
+    pstride = 3 + smax + kmax
+    params = np.zeros((n, pstride))
+    tchange = np.zeros((n, smax))
+    mi32 = np.zeros((n, 8), np.int32)
+    mi64 = np.zeros((n, 2), np.int64)
+    mf64 = np.zeros((n, 4))
+    last = np.zeros(n, np.int64)
+    for i, m in enumerate(models):
+        p = {k: np.asarray(v, dtype=np.float64).reshape(-1) for k, v in m.params.items()}
+        cps = np.atleast_1d(np.asarray(m.changepoints_t, dtype=np.float64))
+        S = len(cps)
+        mask, col = 0, 0
+        beta = p["beta"]
+        for bit, name in ((1, "yearly"), (2, "weekly"), (4, "daily")):
+            if name in m.seasonalities:
+                mask |= bit
+        # fbprophet orders the seasonal columns as the seasonalities were added (yearly, weekly, daily for the defaults)
+        k = 0
+        for bit, name in ((1, "yearly"), (2, "weekly"), (4, "daily")):
+            if sw[name]:
+                if mask & bit:
+                    params[i, 3 + smax + col:3 + smax + col + 2 * orders[name]] = beta[k:k + 2 * orders[name]]
+                    k += 2 * orders[name]
+                col += 2 * orders[name]
+        params[i, 0], params[i, 1], params[i, 2] = p["k"][0], p["m"][0], p["sigma_obs"][0]
+        params[i, 3:3 + S] = p["delta"][:S]
+        tchange[i, :S] = cps
+        start = np.datetime64(m.start, "ns").astype(np.int64)
+        t_scale = np.timedelta64(m.t_scale, "ns").astype(np.int64)
+        hist_max = np.datetime64(max(m.history_dates), "ns").astype(np.int64)
+        mi32[i] = (len(m.history_dates), S, S, mask, 31, 0, 0, 0)
+        mi64[i] = (start, t_scale)
+        mf64[i] = (float(m.y_scale), 0.0 if floor is None else float(np.atleast_1d(floor)[min(i, np.size(floor) - 1)]),
+                   np.nan if cap is None else float(np.atleast_1d(cap)[min(i, np.size(cap) - 1)]), np.nan)
+        last[i] = hist_max
+    fb = FittedBatch(params, tchange, mi32, mi64, mf64, smax, kmax)
+    info = {"logistic": logistic, "multiplicative": mult, "yearly": sw["yearly"] or 0, "weekly": sw["weekly"] or 0,
+            "daily": sw["daily"] or 0, "n_changepoints": smax}
+    return fb, last, info
