@@ -85,8 +85,10 @@ def usable_cores() -> dict:
 
 
 def _build_digest():
+    """Digest of the CUDA sources + nvcc flags the library is built from (time_series_spark_b200/build.py)."""
     try:
-        return open(os.path.join(ROOT, "time_series_spark_b200", "csrc", "_build", "digest.txt")).read().strip()[:16]
+        from time_series_spark_b200.build import _sources_digest
+        return _sources_digest()[:16]
     except Exception:
         return None
 
@@ -265,9 +267,15 @@ def run_gpu(args):
     opts = batched.make_options()          # reference defaults: logistic, multiplicative
     dev = torch.device("cuda", local)
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    group_g = int(os.environ.get("PB200_GROUP", "8"))
-    if group_g not in (8, 16) or os.environ.get("PB200_NO_TAB") == "1":
-        group_g = 0
+    group_env = int(os.environ.get("PB200_GROUP", "-1"))
+    no_tab = os.environ.get("PB200_NO_TAB") == "1"
+
+    def group_of(n):           # the library's dispatch (capi.cu): 8 lanes per series from 16384 series on, 16 below
+        if no_tab:
+            return 0
+        if group_env >= 0:
+            return group_env if group_env in (8, 16, 32) else 0
+        return 8 if n >= int(os.environ.get("PB200_GROUP_MIN", "16384")) else 16
 
     def barrier():
         if world > 1:
@@ -399,7 +407,7 @@ def run_gpu(args):
         "config": {"workload": WORKLOAD, "series_per_gpu": n_mine, "points_per_series": T_POINTS,
                    "global_series": n_job, "parallelism": f"series-sharded x{world} (contiguous row-balanced ranges), no data-path collective",
                    "l2": f"inputs {(b.ds.nbytes + b.y.nbytes) / 1e6:.0f} MB per GPU vs 126 MB L2; every step re-reads them "
-                         f"from HBM (the per-series workspace of the {2368 if not group_g else 4736} resident series is what lives in L2)",
+                         f"from HBM (the per-series workspace of the resident series is what lives in L2)",
                    "mean_objective_evals_per_series": float(evals.mean()), "max_objective_evals": int(evals.max()),
                    "series_with_model": fitted_ok, "fit_kernel_variants": variants, "build_digest": digest},
         "e2e": {"value": n_job * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -411,7 +419,7 @@ def run_gpu(args):
                                  "(max evaluations per series x per-evaluation latency), which does not shrink with the shard"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tps * n_mine) if tps else None, "traffic_source": tsrc, "peak_source": peak_src,
-                     "kernel": _kernel_name(variants, group_g),
+                     "kernel": _kernel_name(variants, group_of(n_mine)),
                      "algorithmic_bytes_per_launch": n_mine * ALG_BYTES_PER_SERIES,
                      "note": "ds/y are read from HBM once per series; the ~700 objective evaluations stream the "
                              "series' y (8 B/point) from the L2-resident workspace: the kernel is FP64-issue / latency bound, "

@@ -47,7 +47,7 @@ def ctxs():
     """name -> context: the grouped day-table kernel (8 and 16 lanes per series), the one-warp-per-series
     kernels (day table, rotation) and the default dispatch (small batch: 4 warps per series)."""
     c = {
-        "g8": _ctx_with_env(PB200_LC0_MAX=1 << 30),
+        "g8": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=8),
         "g16": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=16),
         "tab32": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=0),
         "rot32": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_NO_TAB=1),

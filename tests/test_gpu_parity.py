@@ -332,7 +332,9 @@ def _ctx_with_env(**env):
 
 @pytest.fixture(scope="module")
 def warp_ctx():
-    c = _ctx_with_env(PB200_LC0_MAX=1 << 30)
+    """One warp per series / the grouped kernel with 8 lanes per series for every batch size (the library would give a
+    batch this small 4 warps per series, and the day-table class 16 lanes per series)."""
+    c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=8)
     yield c
     c.close()
 

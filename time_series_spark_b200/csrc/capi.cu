@@ -114,11 +114,13 @@ struct pb200_ctx {
     int lc_max[NLC];
     bool lc_auto = true;   // false when PB200_LC*_MAX pins the CTA width
     bool tab_on = true;    // PB200_NO_TAB=1 disables the seasonal-table variants (A/B runs)
-    int grp_g = 8;         // lanes per series of the grouped day-table kernel (fit_group.cuh); PB200_GROUP=0|8|16, 0 = point_pass_tab
+    int grp_g = -1;        // lanes per series of the grouped day-table kernel (fit_group.cuh); PB200_GROUP=0|8|16|32 pins it
+                           // (0 = point_pass_tab), unset = by batch size: 8 from grp_min series on, 16 below
     DevBuf d_trace;        // trajectory rows of pb200_fit_trace_host
     DevBuf d_nq_all, d_offsets_full;   // pb200_fit_host: per-chunk Newton retry queues, the call's offsets on the device
-    int grp_min = 16384;   // PB200_GROUP_MIN: smallest batch the grouped kernel takes (below it its 4-series warps leave a longer
-                           // straggler tail than one warp per series: r2e, 6250 series: 105 vs 80 ms; 50k: 419 vs 470 ms)
+    int grp_min = 16384;   // PB200_GROUP_MIN: smallest batch that gets 8 lanes per series; smaller ones get 16 (a warp with 4
+                           // series drains longer once the queue is empty).  r2o, ms per step at 6 250 / 12 500 / 50 000 series:
+                           // G = 8: 78 / 113 / 333, G = 16: 73 / 110 / 352, one warp per series (round-1 kernel): 76 / 125 / 455
     int host_chunks = 1;   // PB200_HOST_CHUNKS: series chunks of pb200_fit_host.  Default 1 (one pass): measured on 50k x 1440
                            // (r2j / r2k) 1 / 2 / 4 / 8 chunks = 397 / 407 / 440 / 500 ms -- the 865 MB copy is only ~25 ms at
                            // PCIe 5 speed, and every chunk pays its own straggler drain, which costs more than it hides
@@ -273,8 +275,8 @@ PB200_API pb200_ctx* pb200_create(int device) {
     c->lc_max[2] = 1 << 30;
     c->lc_auto = !(getenv("PB200_LC0_MAX") || getenv("PB200_LC1_MAX"));
     c->tab_on = env_int("PB200_NO_TAB", 0) == 0;
-    c->grp_g = env_int("PB200_GROUP", 8);
-    if (c->grp_g != 8 && c->grp_g != 16 && c->grp_g != 32) c->grp_g = 0;
+    c->grp_g = env_int("PB200_GROUP", -1);
+    if (c->grp_g != -1 && c->grp_g != 8 && c->grp_g != 16 && c->grp_g != 32) c->grp_g = 0;
     c->grp_min = env_int("PB200_GROUP_MIN", 16384);
     return c;
 }
@@ -456,9 +458,9 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
     int* q_head = q_count + NLC * NQ;
 
     const FitOptsDev od = to_dev(opts);
-    // the grouped day-table kernel takes big batches; with the CTA width pinned (tests, A/B runs) it is not second-guessed
+    // lanes per series of the grouped day-table kernel
     // (n_call: series of the whole API call when this is one chunk of it)
-    const int grp_g = (c->tab_on && (!c->lc_auto || std::max<int64_t>(N, n_call) >= c->grp_min)) ? c->grp_g : 0;
+    const int grp_g = !c->tab_on ? 0 : (c->grp_g >= 0 ? c->grp_g : (std::max<int64_t>(N, n_call) >= c->grp_min ? 8 : 16));
     // ---- prep kernel ----
     {
         pb200::PrepArgs pa;

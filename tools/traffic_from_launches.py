@@ -36,8 +36,10 @@ top = max(fits, key=lambda k: fits[k]["ns"])
 big = [m for (i, k), m in per.items() if k == top and m.get("gpu__time_duration.sum", 0.0) > 0.2 * fits[top]["ns"] / fits[top]["n"]]
 rd = sum(m["dram__bytes_read.sum"] for m in big) / len(big)
 wr = sum(m["dram__bytes_write.sum"] for m in big) / len(big)
+sys.path.insert(0, ROOT)
 try:
-    digest = open(os.path.join(ROOT, "time_series_spark_b200", "csrc", "_build", "digest.txt")).read().strip()[:16]
+    from time_series_spark_b200.build import _sources_digest
+    digest = _sources_digest()[:16]
 except Exception:
     digest = None
 d = {"kernel": top, "capture": f"{os.path.relpath(path, ROOT)}: mean of the {len(big)} launches of the kernel that fitted the batch, "
