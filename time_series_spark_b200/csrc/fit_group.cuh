@@ -234,12 +234,11 @@ template <bool LOGI, bool MULT>
 struct GPoint {
     double r, cb, dz, tm;
     // dot: the seasonal term X beta of the point (table entry + weekly part; 1 + X beta in multiplicative mode)
-    // t: for logistic growth t - m_j (the caller keeps it running), for linear growth t itself
     __device__ __forceinline__ void run(const double y, const double t, const double dot, const double e, const double kcj,
                                         const double mcj, const double cap, const bool valid) {
         double g, sig = 0.0;
         if constexpr (LOGI) {
-            tm = t;
+            tm = t - mcj;
             sig = rcp_fastpath(1.0 + e);
             g = cap * sig;
         } else {
@@ -373,11 +372,9 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
             Bw[hh][1] = 0.0;
         }
     }
-    // logistic growth: tt = t - m_j of the step's points w.r.t. the offset m_j in force at the END of the previous step
-    // (advanced by U h per step; a step that crosses changepoints re-bases it); linear growth: t itself
-    double tt[U];
+    double tt[U];                                       // t of the step's points, advanced by U h per step
 #pragma unroll
-    for (int u = 0; u < U; ++u) tt[u] = (double)(i0 + u - U) * h - (LOGI ? mcj : 0.0);
+    for (int u = 0; u < U; ++u) tt[u] = (double)(i0 + u) * h;
     const double hU = (double)U * h;
     auto step = [&](const int m, auto checked_tag) {
         constexpr bool CHECK = decltype(checked_tag)::value;
@@ -414,9 +411,6 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         // one test, and one divergent region for the steps that do (their partial sums are recorded after the
         // step's arithmetic, when the contributions of the step's earlier points are known)
         jlo[0] = j;
-        double tmu[U];                                           // what GPoint::run gets as t
-#pragma unroll
-        for (int u = 0; u < U; ++u) tt[u] += hU;
         if (nb >= i0 + n + U) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -424,11 +418,9 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
                 else ee[u] = 0.0;
                 kcu[u] = kcj;
                 mcu[u] = mcj;
-                tmu[u] = tt[u];
                 jlo[u + 1] = j;
             }
         } else {
-            const double mc0 = mcj;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if constexpr (LOGI) { e = e * qj; ee[u] = e; }
@@ -443,18 +435,13 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
                 }
                 kcu[u] = kcj;
                 mcu[u] = mcj;
-                tmu[u] = LOGI ? tt[u] + (mc0 - mcj) : tt[u];
                 jlo[u + 1] = j;
-            }
-            if constexpr (LOGI) {                              // re-base on the offset now in force
-#pragma unroll
-                for (int u = 0; u < U; ++u) tt[u] += mc0 - mcj;
             }
         }
         if constexpr (LOGI) {
             if (!erec) {                                       // exponent out of the recurrence's range: direct exp
 #pragma unroll
-                for (int u = 0; u < U; ++u) ee[u] = exp_fastpath(-(kcu[u] * tmu[u]));
+                for (int u = 0; u < U; ++u) ee[u] = exp_fastpath(-(kcu[u] * (tt[u] - mcu[u])));
             }
         }
         GPoint<LOGI, MULT> pt[U];
@@ -463,13 +450,15 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
 #pragma unroll
             for (int hh = 0; hh < NH; ++hh) uw[hh][u] = fma(cw[hh], uw[hh][u ^ 1], -uw[hh][u]);
             const double dot = sp[u] + ((uw[0][u] + uw[1][u]) + uw[2][u]);
-            pt[u].run(yv[u], tmu[u], dot, ee[u], kcu[u], mcu[u], cap, val[u]);
+            pt[u].run(yv[u], tt[u], dot, ee[u], kcu[u], mcu[u], cap, val[u]);
             // (beyond the lane's own points c_i = 0 and B must stand still: only the checked tail steps can get there)
             if (!CHECK || n + u < nown) {
 #pragma unroll
                 for (int hh = 0; hh < NH; ++hh) Bw[hh][u] = fma(cw[hh], Bw[hh][u ^ 1], pt[u].cb) - Bw[hh][u];
             }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) tt[u] += hU;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             ss = fma(pt[u].r, pt[u].r, ss);
