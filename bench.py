@@ -58,30 +58,9 @@ def _peaks():
 
 
 def usable_cores() -> dict:
-    """Host threads this process may actually use: CPU affinity intersected with the cgroup CPU quota --
-    NOT os.cpu_count(), which reports the machine (a GPU lease that owns 24 of a box's 128 cores made the
-    round-1 CPU arm look 5.6x slower than the same code on a whole node)."""
-    logical = os.cpu_count() or 1
-    try:
-        aff = len(os.sched_getaffinity(0))
-    except Exception:
-        aff = logical
-    quota = None
-    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
-        try:
-            txt = open(path).read().split()
-            if path.endswith("cpu.max"):
-                if txt[0] != "max":
-                    quota = float(txt[0]) / float(txt[1])
-            else:
-                q = float(txt[0])
-                if q > 0:
-                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
-            break
-        except Exception:
-            continue
-    use = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
-    return {"usable": use, "logical": logical, "affinity": aff, "cgroup_quota": quota}
+    """Host threads this process may actually use (affinity x cgroup quota), see time_series_spark_b200/dist.py."""
+    from time_series_spark_b200.dist import usable_cores as f
+    return f()
 
 
 def _build_digest():
@@ -239,7 +218,7 @@ def _kernel_name(variants: dict, group_g: int, opts_growth_logistic=True) -> str
     logi = "true" if opts_growth_logistic else "false"
     if top == "day_table":
         if group_g:
-            return (f"pb200::grp::fit_group_kernel<{group_g}, {logi}, true>  ({group_g} lanes per series, {32 // group_g} series "
+            return (f"pb200::grp::fit_group_kernel<{group_g}, {logi}, true, true>  ({group_g} lanes per series, {32 // group_g} series "
                     f"per warp, logistic, weekly 3 + daily 4 harmonics, day-table + exp-ratio recurrence)")
         return f"pb200::fit_kernel<32, {logi}, 0, 3, 4, 3>  (warp per series, day-table variant)"
     return {"planes": f"pb200::fit_kernel<32, {logi}, 0, 3, 4, 0>", "rotation": f"pb200::fit_kernel<32, {logi}, 0, 3, 4, 1>",
@@ -537,24 +516,33 @@ def _secondary(args, ctx, lib_stream, dev, rank, world, out, b, barrier, allmax,
             import torch.distributed as dist
             yint = buf_det.yhat_int.reshape(-1)
             cols = [yint, fut.reshape(-1)]
+            nmax = int(allmax(float(yint.numel())))
+            staged = []
+            for c in cols:                                   # receive buffers allocated once, like a job that scores every day
+                pad = torch.zeros(nmax, dtype=c.dtype, device=dev)
+                pad[:c.numel()] = c
+                staged.append((pad, [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None))
+
+            def gather_frame():
+                for pad, bufs in staged:
+                    dist.gather(pad, bufs, dst=0)
+
+            gather_frame()                                   # warm-up: NCCL sets up its peer connections on first use
+            reps = 3
             torch.cuda.synchronize()
             barrier()
             g0 = time.perf_counter()
-            nmax = int(allmax(float(yint.numel())))
-            got = 0
-            for c in cols:
-                pad = torch.zeros(nmax, dtype=c.dtype, device=dev)
-                pad[:c.numel()] = c
-                bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-                dist.gather(pad, bufs, dst=0)
-                if rank == 0:
-                    got += sum(int(x.numel()) * x.element_size() for x in bufs)
-                del bufs, pad
+            for _ in range(reps):
+                gather_frame()
             torch.cuda.synchronize()
             barrier()
-            gs = allmax(time.perf_counter() - g0)
-            ent["nccl_gather_to_rank0"] = {"seconds": gs, "bytes": got, "GB_per_s": got / gs / 1e9 if gs > 0 else None,
+            gs = allmax(time.perf_counter() - g0) / reps
+            got = sum(int(x.numel()) * x.element_size() for _, bufs in staged for x in (bufs or []))
+            remote = got * (world - 1) // world
+            ent["nccl_gather_to_rank0"] = {"seconds": gs, "bytes": got, "bytes_from_peers": remote,
+                                           "GB_per_s_from_peers": remote / gs / 1e9 if gs > 0 else None, "reps": reps,
                                            "columns": "yhat int32 + ds int64 (ids are implied by rank order)"}
+            del staged
             ent["forecast_points_per_s_incl_gather"] = n5 * H / (t_det + gs)
         sec["config5"] = ent
     except Exception as exc:      # the headline must not depend on the secondary metrics

@@ -47,8 +47,8 @@ def ctxs():
     """name -> context: the grouped day-table kernel (8 and 16 lanes per series), the one-warp-per-series
     kernels (day table, rotation) and the default dispatch (small batch: 4 warps per series)."""
     c = {
-        "g8": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=8),
-        "g16": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=16),
+        "g8": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=8, PB200_PLAIN_GROUP=1),
+        "g16": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=16, PB200_PLAIN_GROUP=1),
         "tab32": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=0),
         "rot32": _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_NO_TAB=1),
         "default": L.Context(0),
@@ -104,6 +104,40 @@ def test_lbfgs_trajectory_matches_oracle(ctxs, kernel):
         assert k >= head
         frac.append(k / n)
     print(f"{kernel}: common trajectory prefix / iterations: median {np.median(frac):.2f}, min {np.min(frac):.2f}")
+    assert np.median(frac) >= 0.05
+
+
+@pytest.mark.parametrize("kernel", ["g8", "g16"])
+@pytest.mark.parametrize("growth", ["logistic", "linear"])
+def test_lbfgs_trajectory_plain_grouped_class(ctxs, kernel, growth):
+    """The grouped kernel's class WITHOUT seasonality (config #4's short ragged series, the production path of a
+    large batch of them): same trajectory check, plus the status / iteration count of runs short enough to be
+    identical to the end."""
+    b = synth.config4(n=24)
+    opts, oopts = batched.make_options(growth=growth), po.ProphetOptions(growth=growth)
+    cap = 256
+    fb, tr = batched.fit_batch_trace_host(ctxs[kernel], opts, b.ds, b.y, b.offsets, 0.0, 1.1, trace_cap=cap)
+    vc = ctxs[kernel].last_fit_variant_counts()
+    assert vc[3, 0] == b.n and vc.sum() == b.n, vc
+    frac, same_end = [], 0
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        fr, rows = _oracle_trace(b.ds[a:e], b.y[a:e].astype(np.float64), oopts)
+        n_gpu = int(fb.meta_i32[i, 5])
+        n = min(n_gpu, len(rows), cap)
+        head = min(n, 6)
+        g, o = tr[i], rows
+        assert np.array_equal(g[:head, 3], o[:head, 3]), (kernel, i, g[:head, 3], o[:head, 3])
+        assert np.all(np.abs(g[:head, 1] - o[:head, 1]) <= 1e-11 * np.maximum(1.0, np.abs(o[:head, 1]))), (kernel, i)
+        assert np.all(np.abs(g[:head, 2] - o[:head, 2]) <= 1e-7 * np.abs(o[:head, 2])), (kernel, i)
+        k = _common_prefix(g, o, n)
+        assert k >= head
+        frac.append(k / n)
+        if k == n and n_gpu == len(rows):
+            same_end += 1
+            assert fb.meta_i32[i, 4] == fr.ret
+            assert abs(fb.meta_f64[i, 3] - fr.neg_logp) <= 1e-9 * max(1.0, abs(fr.neg_logp))
+    print(f"plain {kernel} {growth}: common prefix / iterations median {np.median(frac):.2f}; identical to the end: {same_end}/{b.n}")
     assert np.median(frac) >= 0.05
 
 

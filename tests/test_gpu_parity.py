@@ -334,7 +334,7 @@ def _ctx_with_env(**env):
 def warp_ctx():
     """One warp per series / the grouped kernel with 8 lanes per series for every batch size (the library would give a
     batch this small 4 warps per series, and the day-table class 16 lanes per series)."""
-    c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=8)
+    c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=8, PB200_PLAIN_GROUP=1)
     yield c
     c.close()
 
@@ -350,7 +350,7 @@ def warp_ctx_tab32():
 
 @pytest.fixture(scope="module")
 def warp_ctx_g16():
-    c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=16)
+    c = _ctx_with_env(PB200_LC0_MAX=1 << 30, PB200_GROUP=16, PB200_PLAIN_GROUP=1)
     yield c
     c.close()
 
@@ -448,6 +448,87 @@ def test_day_table_other_kernels_objective_and_gradient(warp_ctx_tab32, warp_ctx
     point_pass_tab (PB200_GROUP=0); the default (8 lanes per series) is what every other test of this section runs."""
     case = [c for c in _tab_cases() if c[0] == which][0]
     _check_table_objective(warp_ctx_tab32 if kernel == "tab32" else warp_ctx_g16, warp_ctx_no_tab, case, "logistic_multiplicative")
+
+
+def _plain_cases():
+    c3 = synth.config3(n=8)
+    tiny = synth.config4(n=12, tmin=2, tmax=13)                     # 2 .. 13 points: fewer points than lanes, ncp < 25
+    return {
+        "config4_ragged": (synth.config4(n=24), {}),
+        "tiny_series": (tiny, {}),
+        "long_series_seasonality_off": (c3, {"weekly_seasonality": False, "daily_seasonality": False}),
+        "one_day_of_15min": (_regrid(c3, NS15, 96), {}),             # span < 2 days: every auto seasonality off
+        "short_series": (synth.config4(n=16, tmin=6, tmax=20), {}),
+    }
+
+
+@pytest.mark.parametrize("kernel", ["g8", "g16"])
+@pytest.mark.parametrize("growth", ["logistic", "linear"])
+@pytest.mark.parametrize("which", list(_plain_cases()))
+def test_plain_grouped_class_objective_and_gradient(warp_ctx, warp_ctx_g16, warp_ctx_no_tab, which, growth, kernel):
+    """The grouped kernel's class without seasonality (regular grid, seasonality mask 0: reference config #4) against the
+    oracle and against the one-warp-per-series kernel, at random points around the initial one."""
+    b, kw = _plain_cases()[which]
+    ctx = warp_ctx if kernel == "g8" else warp_ctx_g16
+    opts, oopts = batched.make_options(growth=growth, **kw), po.ProphetOptions(growth=growth, **kw)
+    lay = L.get_layout(opts)
+    rng = np.random.RandomState(11)
+    thetas, preps = [], []
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        y = b.y[a:e].astype(np.float64)
+        p = po.prepare(b.ds[a:e], y, 0.0, y.max() * 1.1, oopts)
+        assert p.K == 1
+        th = po.initial_theta(p) + 0.05 * rng.randn(p.S + p.K + 3)
+        row = np.zeros(lay.pstride)
+        row[:th.size] = th
+        thetas.append(row)
+        preps.append((p, th))
+    th = np.array(thetas)
+    f, g, mi = batched.objective_host(ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1, th)
+    counts = ctx.last_fit_variant_counts()
+    assert counts[3, 0] == b.n and counts.sum() == b.n, (which, counts)
+    f0, g0, _ = batched.objective_host(warp_ctx_no_tab, opts, b.ds, b.y, b.offsets, 0.0, 1.1, th)
+    assert warp_ctx_no_tab.last_fit_variant_counts()[0, 0] == b.n
+    for i, (p, t) in enumerate(preps):
+        err, fo, go = po.neg_logp_grad(t, p)
+        assert err == 0 and mi[i, 4] == 0 and mi[i, 3] == 0
+        assert abs(f[i] - fo) <= 1e-10 * max(1.0, abs(fo)), (which, i, f[i], fo)
+        gd = np.max(np.abs(g[i, :t.size] - go)) / max(1.0, np.max(np.abs(go)))
+        assert gd <= 1e-8, (which, i, gd)
+        assert abs(f[i] - f0[i]) <= 1e-10 * max(1.0, abs(fo))
+        assert np.max(np.abs(g[i] - g0[i])) <= 1e-9 * max(1.0, np.max(np.abs(go)))
+
+
+@pytest.mark.parametrize("which", ["config4_ragged", "short_series"])
+def test_plain_grouped_class_fit(warp_ctx, warp_ctx_no_tab, which):
+    """Fits of the class: same statuses as the one-warp-per-series kernel wherever both ran the same trajectory, objective at the
+    optimum within the algorithm's own sensitivity, deterministic, batch-order independent."""
+    b, kw = _plain_cases()[which]
+    opts = batched.make_options(**kw)
+    fa = batched.fit_batch_host(warp_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    assert warp_ctx.last_fit_variant_counts()[3, 0] == b.n
+    fb = batched.fit_batch_host(warp_ctx, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    assert np.array_equal(fa.params, fb.params) and np.array_equal(fa.meta_i32, fb.meta_i32)
+    f0 = batched.fit_batch_host(warp_ctx_no_tab, opts, b.ds, b.y, b.offsets, 0.0, 1.1)
+    ok = (fa.meta_i32[:, 4] >= 0) & (f0.meta_i32[:, 4] >= 0)
+    assert ok.sum() >= b.n - 1
+    rel = np.abs(fa.meta_f64[ok, 3] - f0.meta_f64[ok, 3]) / np.maximum(1.0, np.abs(f0.meta_f64[ok, 3]))
+    assert np.median(rel) <= 1e-6 and rel.max() <= 5e-3, rel
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        fr = po.fit(b.ds[a:e], b.y[a:e].astype(np.float64), opts=po.ProphetOptions(**kw))
+        if fa.meta_i32[i, 4] >= 0 and fr.ret >= 0:
+            assert abs(fa.meta_f64[i, 3] - fr.neg_logp) <= 5e-3 * max(1.0, abs(fr.neg_logp)), (i, fa.meta_f64[i, 3], fr.neg_logp)
+    # a series' result does not depend on its neighbours in the warp: reversed batch
+    T = np.diff(b.offsets)
+    order = np.arange(b.n)[::-1]
+    offs = np.zeros(b.n + 1, np.int64)
+    np.cumsum(T[order], out=offs[1:])
+    ds_r = np.concatenate([b.ds[b.offsets[i]:b.offsets[i + 1]] for i in order])
+    y_r = np.concatenate([b.y[b.offsets[i]:b.offsets[i + 1]] for i in order])
+    fr_ = batched.fit_batch_host(warp_ctx, opts, ds_r, y_r, offs, 0.0, 1.1)
+    assert np.array_equal(fr_.params[::-1], fa.params) and np.array_equal(fr_.meta_i32[::-1, 4:7], fa.meta_i32[:, 4:7])
 
 
 @pytest.mark.parametrize("which", ["day_table_15min", "week_table_hourly"])

@@ -118,6 +118,9 @@ struct pb200_ctx {
                            // (0 = point_pass_tab), unset = by batch size: 8 from grp_min series on, 16 below
     DevBuf d_trace;        // trajectory rows of pb200_fit_trace_host
     DevBuf d_nq_all, d_offsets_full;   // pb200_fit_host: per-chunk Newton retry queues, the call's offsets on the device
+    int plain_grp = 0;     // PB200_PLAIN_GROUP=1: the class WITHOUT seasonality (regular grid; reference config #4) on the grouped kernel
+                           // too.  Off: measured 6 % faster than one warp per series at 500k short series, 3 % slower at 100k and
+                           // 35 % slower at 30k (r2s) -- its rounds are longer, and small batches are latency bound
     int grp_min = 16384;   // PB200_GROUP_MIN: smallest batch that gets 8 lanes per series; smaller ones get 16 (a warp with 4
                            // series drains longer once the queue is empty).  r2o, ms per step at 6 250 / 12 500 / 50 000 series:
                            // G = 8: 78 / 113 / 333, G = 16: 73 / 110 / 352, one warp per series (round-1 kernel): 76 / 125 / 455
@@ -278,6 +281,7 @@ PB200_API pb200_ctx* pb200_create(int device) {
     c->grp_g = env_int("PB200_GROUP", -1);
     if (c->grp_g != -1 && c->grp_g != 8 && c->grp_g != 16 && c->grp_g != 32) c->grp_g = 0;
     c->grp_min = env_int("PB200_GROUP_MIN", 16384);
+    c->plain_grp = env_int("PB200_PLAIN_GROUP", 0) != 0;
     return c;
 }
 
@@ -484,6 +488,7 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
         for (int lc = 0; lc < NLC; ++lc)
             if (c->tab_on && LC_NT[lc] == 32) pa.tab_lc_mask |= 1 << lc;
         pa.grp_g = grp_g;
+        pa.grp_plain = (c->plain_grp && grp_g > 0) ? 1 : 0;
         pa.newton_only = (opts->algorithm == PB200_ALG_NEWTON && !d_theta_in) ? 1 : 0;
         pa.nq_count = nq;
         pa.nq_items = nq + 2;
@@ -514,8 +519,9 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
             g.on = false;
             g.grouped = false;
             if (lc_n[lc] == 0) continue;
-            if (reg && mask == 0) continue;       // no Fourier features: nothing to regenerate
-            if (reg >= 2 && (mask != 6 || LC_NT[lc] != 32 || !c->tab_on)) continue;   // seasonal-table variants
+            const bool plain_grp = reg == 3 && mask == 0 && grp_g > 0;   // grouped kernel's class without seasonality
+            if (reg && mask == 0 && !plain_grp) continue;                // no Fourier features: nothing to regenerate
+            if (reg >= 2 && ((mask != 6 && !plain_grp) || LC_NT[lc] != 32 || !c->tab_on)) continue;   // seasonal-table variants
             auto impossible = [&](int bit, int sw) { return (sw == 0 && (mask & bit)) || (sw == 1 && !(mask & bit)); };
             if (impossible(1, opts->yearly) || impossible(2, opts->weekly) || impossible(4, opts->daily)) continue;
             const int NT = LC_NT[lc];
@@ -534,7 +540,7 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
             if (reg == 3 && grp_g > 0) {
                 // grouped day-table kernel: one warp per CTA, 32 / grp_g series per warp, one workspace slot per series
                 const int nser = 32 / grp_g;
-                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, dummy, 0, w.stream, &occ));
+                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, mask != 0, dummy, 0, w.stream, &occ));
                 if (occ < 1) return fail(PB200_E_UNSUPPORTED, "grouped fit kernel does not fit on an SM");
                 g.grouped = true;
                 g.slice = pb200::fit_group_plane_doubles(lc_tmax[lc], grp_g);           // doubles per slot
@@ -588,7 +594,7 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
             fa.nq_items = opts->algorithm == PB200_ALG_LBFGS_NEWTON ? nq + 2 : nullptr;
             fa.o = od;
             if (g.grouped) {
-                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, fa, g.grid, w.stream, nullptr));
+                CK(pb200::launch_fit_group(grp_g, opts->growth, opts->multiplicative ? 1 : 0, mask != 0, fa, g.grid, w.stream, nullptr));
             } else {
                 CK(LAUNCH[mask](NT, opts->growth, reg, fa, g.grid, smem, w.stream, nullptr));
             }

@@ -35,23 +35,31 @@ namespace pb200 {
 namespace grp {
 
 constexpr int GK = 14, GKW = 6, GKD = 8; // weekly 3 + daily 4 harmonics
+// SEAS = false: the class without any seasonality (regular grid, span under two days: reference config #4's short series) --
+// the same state machine with no table, no weekly recurrences and the single all-zero feature column fbprophet keeps
+template <bool SEAS> constexpr int gkx() { return SEAS ? GK : 1; }
 
 constexpr int ST_IDLE = 0, ST_FIRST = 1, ST_SEARCH = 2, ST_OBJ = 3;
 
-template <int G>
+// SEAS = false (the class without seasonality) drops the table and shortens the vectors: 3.7 instead of 5.8 KB per series,
+// the difference between 9 and 14 resident warps per SM (r2s: that class's time is inversely proportional to them)
+template <int G, bool SEAS>
 struct GState {
+    static constexpr int PPAD = SEAS ? GPPAD : GPPAD_PLAIN;
+    static constexpr int PT = SEAS ? GPT : 2;        // (without a table: the scratch of the pass's two totals)
+    static constexpr int TOTSS = SEAS ? GK : 1;      // where the pass leaves the residual sum of squares: stab[TOTSS]
     LSState ls;
     double cap_s, sigma, hstep, zmax;
     int T, S, ncp, chunk, tabP, tabPL, series, state, exprec, st0, i1max, pad_;
     double kc[GSEG], mc[GSEG], tc[GSEG], qs[GSEG], bndU[GSEG], bndV[GSEG];
     int bidx[GSEG];
-    alignas(16) double bcoef[16];
+    alignas(16) double bcoef[SEAS ? 16 : 2];
     double hrho[8];
     alignas(16) double rotw[2];          // (sin, cos) of one grid step's advance of the weekly angle
     alignas(16) double rotd[2];          // ... of the daily angle
-    alignas(16) double stab[GPT];        // s_p: daily part of X beta at table phase p
-    alignas(16) double rtab[GPT];        // R_p: residual bins; stab / rtab double as the reduction scratch
-    alignas(16) double vec[6][GPPAD];    // x g p x_trial g_trial p_prev (roles in ls.ix ...)
+    alignas(16) double stab[PT];         // s_p: daily part of X beta at table phase p
+    alignas(16) double rtab[PT];         // R_p: residual bins; stab / rtab double as the reduction scratch
+    alignas(16) double vec[6][PPAD];     // x g p x_trial g_trial p_prev (roles in ls.ix ...)
 };
 
 // per-lane constants of a lane's chunk of ITS series, kept in registers between evaluations (g_fetch leaves them in
@@ -63,9 +71,9 @@ struct LanePhase {
     int j0;             // trend segment of the point before the lane's chunk
 };
 
-template <int G>
+template <int G, bool SEAS>
 inline size_t group_smem_bytes() {
-    return (size_t)(32 / G) * ((sizeof(GState<G>) + 15) & ~(size_t)15) + (size_t)2 * (grp_u(G) / 2) * 32 * 16   // + cp.async ring
+    return (size_t)(32 / G) * ((sizeof(GState<G, SEAS>) + 15) & ~(size_t)15) + (size_t)2 * (grp_u(G) / 2) * 32 * 16   // + cp.async ring
            + sizeof(FitOptsDev);                                                                          // + the options
 }
 // global workspace per series slot (doubles): y pairs, then history Y[5], S[5]
@@ -75,19 +83,19 @@ __host__ __device__ inline size_t group_plane_doubles(int tmax, int G) {
 }
 constexpr int GHIST = 2 * HMAX * GPPAD;
 
-template <int G>
-__device__ __forceinline__ GState<G>& gstate(int gi) {
-    return *reinterpret_cast<GState<G>*>(pb200_smem + (size_t)gi * ((sizeof(GState<G>) + 15) & ~(size_t)15));
+template <int G, bool SEAS>
+__device__ __forceinline__ GState<G, SEAS>& gstate(int gi) {
+    return *reinterpret_cast<GState<G, SEAS>*>(pb200_smem + (size_t)gi * ((sizeof(GState<G, SEAS>) + 15) & ~(size_t)15));
 }
-template <int G>
+template <int G, bool SEAS>
 __device__ __forceinline__ double2* gring() {
-    return reinterpret_cast<double2*>(pb200_smem + (size_t)(32 / G) * ((sizeof(GState<G>) + 15) & ~(size_t)15));
+    return reinterpret_cast<double2*>(pb200_smem + (size_t)(32 / G) * ((sizeof(GState<G, SEAS>) + 15) & ~(size_t)15));
 }
 // the fit options, copied out of the kernel parameters once per warp (the optimiser's routines take them by reference;
 // a reference into the parameter bank would force a local-memory copy that misses L1 on every use: r2c profile)
-template <int G>
+template <int G, bool SEAS>
 __device__ __forceinline__ FitOptsDev& gopts() {
-    return *reinterpret_cast<FitOptsDev*>(reinterpret_cast<unsigned char*>(gring<G>()) + (size_t)2 * (grp_u(G) / 2) * 32 * 16);
+    return *reinterpret_cast<FitOptsDev*>(reinterpret_cast<unsigned char*>(gring<G, SEAS>()) + (size_t)2 * (grp_u(G) / 2) * 32 * 16);
 }
 
 __device__ __forceinline__ void cp_async16_sa(const unsigned smem_addr, const void* gsrc) {
@@ -130,11 +138,11 @@ __device__ __forceinline__ double gscan_excl_rev(double v, const int gl, const u
     }
     return inc - v;
 }
-template <int G>
+template <int G, int PPAD>
 __device__ __noinline__ double gvdot(const double* a, const double* b, const int P, const int gl, const unsigned gm) {
     double s = 0.0;
 #pragma unroll
-    for (int u = 0; u < (GPPAD + G - 1) / G; ++u) {
+    for (int u = 0; u < (PPAD + G - 1) / G; ++u) {
         const int q = gl + u * G;
         if (q < P) s = fma(a[q], b[q], s);
     }
@@ -144,8 +152,8 @@ __device__ __noinline__ double gvdot(const double* a, const double* b, const int
 // ---------------------------------------------------------------------------------------
 // evaluation, part 1: trend segments of theta (rate, offset, per-step exp ratio), sigma, beta
 // ---------------------------------------------------------------------------------------
-template <int G, bool LOGI>
-__device__ __noinline__ void g_eval_setup(GState<G>& s, const double* xv, const int gl, const unsigned gm) {
+template <int G, bool LOGI, bool SEAS>
+__device__ __noinline__ void g_eval_setup(GState<G, SEAS>& s, const double* xv, const int gl, const unsigned gm) {
     constexpr int NS = GSEG / G;
     const int S = s.S, jb = gl * NS;
     const double k = xv[0], m = xv[1];
@@ -219,9 +227,9 @@ __device__ __noinline__ void g_eval_setup(GState<G>& s, const double* xv, const 
         if (gl == 0) s.exprec = 0;
     }
 #pragma unroll
-    for (int u = 0; u < (GK + G - 1) / G; ++u) {
+    for (int u = 0; u < (gkx<SEAS>() + G - 1) / G; ++u) {
         const int q = gl + u * G;
-        if (q < GK) s.bcoef[q] = xv[3 + S + q];
+        if (q < gkx<SEAS>()) s.bcoef[q] = xv[3 + S + q];
     }
     __syncwarp(gm);
 }
@@ -264,15 +272,15 @@ struct GPoint {
 // ---------------------------------------------------------------------------------------
 // evaluation, part 2: the pass over the points (all lanes of the warp, every active group)
 // ---------------------------------------------------------------------------------------
-template <int G, bool LOGI, bool MULT, int U>
-__device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, const bool active, const int gl, const int lane,
+template <int G, bool LOGI, bool MULT, bool SEAS, int U>
+__device__ __noinline__ void g_point_pass(GState<G, SEAS>& s, const double* plane, const bool active, const int gl, const int lane,
                                           const unsigned gm, const LanePhase lp) {
     static_assert(U == 2 || U == 4, "points per lane per step");
-    const int P = active ? s.tabP : GPT, PL = active ? s.tabPL : 0;     // (an idle group's lanes only keep step)
+    const int P = active ? s.tabP : GState<G, SEAS>::PT, PL = active ? s.tabPL : 0;     // (an idle group's lanes only keep step)
     const double2 rct = *reinterpret_cast<const double2*>(s.rotd);
     const double2 w0 = lp.dph;
     // ---- seasonal table of this evaluation; residual bins cleared ----
-    if (active) {
+    if (SEAS && active) {
         double2 w = w0;
         int p = gl * PL;
 #pragma unroll 2
@@ -303,8 +311,10 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     int j = active ? lp.j0 : 0;                        // trend segment of the point before the chunk
     const int j0 = j;
     double gacc[GK];
+    if constexpr (SEAS) {
 #pragma unroll
-    for (int q = 0; q < GK; ++q) gacc[q] = 0.0;
+        for (int q = 0; q < GK; ++q) gacc[q] = 0.0;
+    }
     double ss = 0.0, locU = 0.0, locV = 0.0;
     int nb = (active && j < S) ? s.bidx[j] : 0x7fffffff;
     double kcj = s.kc[j], mcj = s.mc[j];
@@ -327,7 +337,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     nfull = min(nfull, nstep);
     // cp.async ring: 2 stages of U points per lane (stage st, half q: row (st (U / 2) + q) of 32 double2).  The 32-bit
     // shared-window address is taken once: inside the loop the generic-to-shared conversion cost an S2R per step (r2c profile)
-    double2* const ring = gring<G>() + lane;
+    double2* const ring = gring<G, SEAS>() + lane;
     const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
     constexpr unsigned STAGE_B = (U / 2) * 32 * 16;
     const double2* gsrc = reinterpret_cast<const double2*>(plane) + gl * (U / 2);   // step m of this lane: gsrc[m G (U / 2) + q]
@@ -337,7 +347,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     }
     cp_async_commit();
     const double2* gnext = gsrc + G * (U / 2);
-    int pb = P > 0 ? i0 % P : 0;
+    int pb = (SEAS && P > 0) ? i0 % P : 0;
     // The weekly part of the seasonal term and of the beta gradient WITHOUT the six weekly features per point.  Every
     // harmonic h of the weekly angle obeys the three-term recurrence y(i + 1) = c_h y(i) - y(i - 1), c_h = 2 cos(h delta),
     // for its sine, its cosine and therefore for u_h(i) = beta_sh sin + beta_ch cos:
@@ -354,7 +364,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
     constexpr int NH = GKW / 2;
     double uw[NH][2], Bw[NH][2], cw[NH];
     const int nown = active ? 2 * ((npts + 1) >> 1) : 0;       // this lane's own points (padded to whole steps)
-    {
+    if constexpr (SEAS) {
         const double2 rcw = *reinterpret_cast<const double2*>(s.rotw);
         double Xr[GKW], X0[GKW], X1[GKW];
         harmonics<3>(rcw, Xr);                              // cos(h delta) at the odd positions
@@ -390,8 +400,10 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         cp_async_wait<1>();
         double yv[U];
         bool val[U];
-        int pu[U], jlo[U + 1];
-        double sp[U], Rv[U], ee[U], kcu[U], mcu[U];
+        [[maybe_unused]] int pu[U];
+        [[maybe_unused]] double sp[U], Rv[U];
+        int jlo[U + 1];
+        double ee[U], kcu[U], mcu[U];
 #pragma unroll
         for (int q = 0; q < U / 2; ++q) {
             const double2 v = cur[q * 32];
@@ -401,10 +413,12 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             val[u] = CHECK ? n + u < npts : true;
-            pu[u] = pb;
-            pb = (pb + 1 == P) ? 0 : pb + 1;
-            sp[u] = s.stab[pu[u]];
-            Rv[u] = s.rtab[pu[u]];
+            if constexpr (SEAS) {
+                pu[u] = pb;
+                pb = (pb + 1 == P) ? 0 : pb + 1;
+                sp[u] = s.stab[pu[u]];
+                Rv[u] = s.rtab[pu[u]];
+            }
         }
         // exp ratio recurrence: the step INTO a point uses the rate of the segment the previous point is in; then the
         // changepoints AT the point switch rate, offset and ratio.  Nearly all steps hold no changepoint of this lane:
@@ -444,15 +458,18 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
                 for (int u = 0; u < U; ++u) ee[u] = exp_fastpath(-(kcu[u] * (tt[u] - mcu[u])));
             }
         }
-        GPoint<LOGI, MULT> pt[U];
+        GPoint<LOGI, (MULT && SEAS)> pt[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            double dot = 0.0;                                  // no seasonality: additive with a zero seasonal term
+            if constexpr (SEAS) {
 #pragma unroll
-            for (int hh = 0; hh < NH; ++hh) uw[hh][u] = fma(cw[hh], uw[hh][u ^ 1], -uw[hh][u]);
-            const double dot = sp[u] + ((uw[0][u] + uw[1][u]) + uw[2][u]);
+                for (int hh = 0; hh < NH; ++hh) uw[hh][u] = fma(cw[hh], uw[hh][u ^ 1], -uw[hh][u]);
+                dot = sp[u] + ((uw[0][u] + uw[1][u]) + uw[2][u]);
+            }
             pt[u].run(yv[u], tt[u], dot, ee[u], kcu[u], mcu[u], cap, val[u]);
             // (beyond the lane's own points c_i = 0 and B must stand still: only the checked tail steps can get there)
-            if (!CHECK || n + u < nown) {
+            if (SEAS && (!CHECK || n + u < nown)) {
 #pragma unroll
                 for (int hh = 0; hh < NH; ++hh) Bw[hh][u] = fma(cw[hh], Bw[hh][u ^ 1], pt[u].cb) - Bw[hh][u];
             }
@@ -462,7 +479,9 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             ss = fma(pt[u].r, pt[u].r, ss);
-            if (val[u]) s.rtab[pu[u]] = Rv[u] + pt[u].cb;      // R_p += c_i (bins of a step are pairwise distinct)
+            if constexpr (SEAS) {
+                if (val[u]) s.rtab[pu[u]] = Rv[u] + pt[u].cb;  // R_p += c_i (bins of a step are pairwise distinct)
+            }
         }
         double preU[U + 1], preV[U + 1];
         preU[0] = locU;
@@ -484,14 +503,14 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
                 }
             }
         }
-        __syncwarp();
+        if constexpr (SEAS) __syncwarp();                      // (the bins: all lanes of the warp step together)
     };
     int m = 0;
 #pragma unroll 1
     for (; m < nfull; ++m) step(m, std::false_type{});
 #pragma unroll 1
     for (; m < nstep; ++m) step(m, std::true_type{});
-    {   // weekly beta gradient: close the Clenshaw sums with the features of the lane's last two (padded) points
+    if constexpr (SEAS) {   // weekly beta gradient: close the Clenshaw sums with the features of the lane's last two (padded) points
         const double2 rcw = *reinterpret_cast<const double2*>(s.rotw);
         double Y2[GKW], Y1[GKW];
         double2 w = lp.wend;                                // weekly angle at point i0 + nown - 2
@@ -507,7 +526,7 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         }
     }
     // ---- table features' beta gradient from the residual bins ----
-    if (active) {
+    if (SEAS && active) {
         double2 w = w0;
         int p = gl * PL;
 #pragma unroll 2
@@ -536,10 +555,18 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
         if (gl == 0) { s.bndU[S] = totU; s.bndV[S] = totV; }
     }
     __syncwarp();
+    if constexpr (!SEAS) {
+        // only the residual sum of squares to total; the zero column's gradient sum is zero
+        ss = gsum<G>(ss, gm);
+        double* scr = s.stab;                                   // (stab and rtab are contiguous: value v at scr[v])
+        if (active && gl == 0) { scr[0] = 0.0; scr[GState<G, SEAS>::TOTSS] = ss; }
+        __syncwarp();
+        return;
+    }
     // ---- group totals of (gacc[0..13], ss): transposed through the (now dead) table storage ----
     {
         double* scr = s.stab;                                   // stab and rtab are contiguous: 2 GPT doubles
-        static_assert(15 * 8 <= 2 * GPT, "reduction scratch");
+        static_assert(!SEAS || 15 * 8 <= 2 * GState<G, SEAS>::PT, "reduction scratch");
         // fold the group's upper blocks of eight lanes onto the lowest block, top block first (fixed order)
 #pragma unroll
         for (int blk = G / 8 - 1; blk >= 1; --blk) {
@@ -588,13 +615,13 @@ __device__ __noinline__ void g_point_pass(GState<G>& s, const double* plane, con
 // ---------------------------------------------------------------------------------------
 // evaluation, part 3: objective value and gradient from the pass's sums; returns err (group-uniform)
 // ---------------------------------------------------------------------------------------
-template <int G, bool LOGI>
-__device__ __noinline__ int g_eval_finalize(GState<G>& s, const double* xv, double* gv, const int gl, const unsigned gm,
+template <int G, bool LOGI, bool SEAS>
+__device__ __noinline__ int g_eval_finalize(GState<G, SEAS>& s, const double* xv, double* gv, const int gl, const unsigned gm,
                                             const double tau, const double rtau, const double inv_seas2, double* f_out) {
     constexpr int NS = GSEG / G;
     const int S = s.S, T = s.T, jb = gl * NS;
     const double* tot = s.stab;                     // value v of the pass: tot[v], v < 14 beta sums, tot[14] = ss
-    const double ss = tot[GK];
+    const double ss = tot[GState<G, SEAS>::TOTSS];
     const double sigma = s.sigma;
     const double inv_s2 = rcp_any(sigma * sigma);
     const double scale = -inv_s2;
@@ -710,9 +737,9 @@ __device__ __noinline__ int g_eval_finalize(GState<G>& s, const double* xv, doub
     // beta gradient and prior
     double pb = 0.0;
 #pragma unroll
-    for (int u = 0; u < (GK + G - 1) / G; ++u) {
+    for (int u = 0; u < (gkx<SEAS>() + G - 1) / G; ++u) {
         const int q = gl + u * G;
-        if (q < GK) {
+        if (q < gkx<SEAS>()) {
             const double b = xv[3 + S + q];
             const double gb = scale * tot[q] + b * inv_seas2;
             gv[3 + S + q] = gb;
@@ -741,37 +768,37 @@ __device__ __noinline__ int g_eval_finalize(GState<G>& s, const double* xv, doub
 // ---------------------------------------------------------------------------------------
 // Stan's L-BFGS over the group's LSState (see fit_kernel.cuh for the routine-by-routine mapping)
 // ---------------------------------------------------------------------------------------
-template <int G>
-__device__ __noinline__ void g_make_trial(GState<G>& s, const double alpha, const int P, const int gl, const unsigned gm) {
+template <int G, bool SEAS>
+__device__ __noinline__ void g_make_trial(GState<G, SEAS>& s, const double alpha, const int P, const int gl, const unsigned gm) {
     const double* x = s.vec[s.ls.ix];
     const double* p = s.vec[s.ls.ip];
     double* xt = s.vec[s.ls.ixt];
 #pragma unroll
-    for (int u = 0; u < (GPPAD + G - 1) / G; ++u) {
+    for (int u = 0; u < (GState<G, SEAS>::PPAD + G - 1) / G; ++u) {
         const int q = gl + u * G;
         if (q < P) xt[q] = x[q] + alpha * p[q];
     }
     __syncwarp(gm);
 }
 
-template <int G>
-__device__ __noinline__ void g_ls_begin(GState<G>& s, const int gl, const unsigned gm, const int P, const double init_alpha) {
+template <int G, bool SEAS>
+__device__ __noinline__ void g_ls_begin(GState<G, SEAS>& s, const int gl, const unsigned gm, const int P, const double init_alpha) {
     LSState& ls = s.ls;
     const double minAlpha = 1e-12;
     const double* g = s.vec[ls.ig];
     double* p = s.vec[ls.ip];
     if (ls.resetB) {
 #pragma unroll
-        for (int u = 0; u < (GPPAD + G - 1) / G; ++u) {
+        for (int u = 0; u < (GState<G, SEAS>::PPAD + G - 1) / G; ++u) {
             const int q = gl + u * G;
             if (q < P) p[q] = -g[q];
         }
         __syncwarp(gm);
     }
-    const double dfp = gvdot<G>(g, p, P, gl, gm);
+    const double dfp = gvdot<G, GState<G, SEAS>::PPAD>(g, p, P, gl, gm);
     double alpha;
     if (ls.iters > 1 && ls.resetB != 2) {
-        const double dprev = gvdot<G>(s.vec[ls.igt], s.vec[ls.ipp], P, gl, gm);
+        const double dprev = gvdot<G, GState<G, SEAS>::PPAD>(s.vec[ls.igt], s.vec[ls.ipp], P, gl, gm);
         alpha = fmin(1.0, 1.01 * cubic_interp(dprev, ls.alphak_1, ls.fk - ls.fk_1, dfp, minAlpha, 1.0));
     } else {
         alpha = init_alpha;
@@ -782,11 +809,11 @@ __device__ __noinline__ void g_ls_begin(GState<G>& s, const int gl, const unsign
         ls.nits = 0; ls.lsRestarts = 0; ls.phase = PH_LS;
     }
     __syncwarp(gm);
-    g_make_trial<G>(s, alpha, P, gl, gm);
+    g_make_trial<G, SEAS>(s, alpha, P, gl, gm);
 }
 
-template <int G>
-__device__ __noinline__ int g_ls_step(GState<G>& s, const int gl, const unsigned gm, const int P, const int err) {
+template <int G, bool SEAS>
+__device__ __noinline__ int g_ls_step(GState<G, SEAS>& s, const int gl, const unsigned gm, const int P, const int err) {
     LSState& ls = s.ls;
     const double c1 = 1e-4, c2 = 0.9, min_range = 1e-16;
     const int maxLSIts = 20, maxLSRestarts = 10;
@@ -805,10 +832,10 @@ __device__ __noinline__ int g_ls_step(GState<G>& s, const int gl, const unsigned
             __syncwarp(gm);
             if (gl == 0) { ls.alpha = alpha; ls.lsRestarts += 1; }
             __syncwarp(gm);
-            g_make_trial<G>(s, alpha, P, gl, gm);
+            g_make_trial<G, SEAS>(s, alpha, P, gl, gm);
             return ACT_EVAL;
         }
-        const double newDFp = gvdot<G>(s.vec[ls.igt], s.vec[ls.ip], P, gl, gm);
+        const double newDFp = gvdot<G, GState<G, SEAS>::PPAD>(s.vec[ls.igt], s.vec[ls.ip], P, gl, gm);
         if (ft > fk + alpha * c1dfp || (ft >= prevF && nits > 0)) {
             alo = alpha0; aloF = prevF; aloD = prevDFp;
             ahi = alpha; ahiF = ft; ahiD = newDFp;
@@ -826,7 +853,7 @@ __device__ __noinline__ int g_ls_step(GState<G>& s, const int gl, const unsigned
                 ls.lsRestarts = 0;
             }
             __syncwarp(gm);
-            g_make_trial<G>(s, a10, P, gl, gm);
+            g_make_trial<G, SEAS>(s, a10, P, gl, gm);
             return ACT_EVAL;
         }
         itNum = 0;
@@ -839,10 +866,10 @@ __device__ __noinline__ int g_ls_step(GState<G>& s, const int gl, const unsigned
             __syncwarp(gm);
             if (gl == 0) ls.alpha = alpha;
             __syncwarp(gm);
-            g_make_trial<G>(s, alpha, P, gl, gm);
+            g_make_trial<G, SEAS>(s, alpha, P, gl, gm);
             return ACT_EVAL;
         }
-        const double newDFp = gvdot<G>(s.vec[ls.igt], s.vec[ls.ip], P, gl, gm);
+        const double newDFp = gvdot<G, GState<G, SEAS>::PPAD>(s.vec[ls.igt], s.vec[ls.ip], P, gl, gm);
         if (ft > (fk + alpha * c1dfp) || ft >= aloF) {
             ahi = alpha; ahiF = ft; ahiD = newDFp;
         } else {
@@ -876,15 +903,15 @@ __device__ __noinline__ int g_ls_step(GState<G>& s, const int gl, const unsigned
         ls.alo = alo; ls.aloF = aloF; ls.aloD = aloD; ls.ahi = ahi; ls.ahiF = ahiF; ls.ahiD = ahiD;
     }
     __syncwarp(gm);
-    g_make_trial<G>(s, alpha, P, gl, gm);
+    g_make_trial<G, SEAS>(s, alpha, P, gl, gm);
     return ACT_EVAL;
 }
 
 // the rest of BFGSMinimizer::step after an accepted line search; history Y[5], S[5] in global memory `hist`
-template <int G>
-__device__ __noinline__ int g_post_accept(GState<G>& s, double* hist, const int gl, const unsigned gm, const int P,
+template <int G, bool SEAS>
+__device__ __noinline__ int g_post_accept(GState<G, SEAS>& s, double* hist, const int gl, const unsigned gm, const int P,
                                           const FitOptsDev& o, double* trace, const int trace_cap) {
-    constexpr int NV = (GPPAD + G - 1) / G;
+    constexpr int NV = (GState<G, SEAS>::PPAD + G - 1) / G;
     LSState& ls = s.ls;
     double* HY = hist;
     double* HS = hist + HMAX * GPPAD;
@@ -1029,8 +1056,8 @@ __device__ __noinline__ int g_post_accept(GState<G>& s, double* hist, const int 
 // fetch the next series of the queue into this group's slot: stage y, phases, changepoints, initial point
 // returns false when the queue is exhausted
 // ---------------------------------------------------------------------------------------
-template <int G, bool LOGI>
-__device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* plane, const int gl, const unsigned gm) {
+template <int G, bool LOGI, bool SEAS>
+__device__ __noinline__ bool g_fetch(GState<G, SEAS>& s, const FitArgs& a, double* plane, const int gl, const unsigned gm) {
     if (gl == 0) {
         const int pos = atomicAdd(a.q_head, 1);
         s.series = pos < *a.q_count ? a.q_items[pos] : -1;
@@ -1046,8 +1073,8 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
     const double y_scale = mf[0], fl = mf[1], capv = mf[2];
     const long long off = a.offsets[sidx];
     const long long step = a.ds[off + 1] - a.ds[off];
-    const int tabP = (int)((86400LL * 1000000000LL) / step);
-    const int chunk = grp_chunk(T, tabP, G, grp_u(G));
+    const int tabP = SEAS ? (int)((86400LL * 1000000000LL) / step) : 0;
+    const int chunk = SEAS ? grp_chunk(T, tabP, G, grp_u(G)) : grp_chunk_plain(T, G);
     const double dts = (double)tscale;
     const double cap_s = LOGI ? (capv - fl) / y_scale : 0.0;
     const int PL = (tabP + G - 1) / G;
@@ -1055,12 +1082,14 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
     if (gl == 0) {
         s.T = T; s.S = S; s.ncp = ncp; s.chunk = chunk; s.tabP = tabP; s.tabPL = PL;
         s.cap_s = cap_s; s.hstep = (double)step / dts; s.st0 = st0; s.i1max = i1max; s.exprec = 0;
-        const double dt_d = (1e-9 * (double)step) / 86400.0;
-        double s_, c_;
-        sincos(TWO_PI_FL * dt_d / 7.0, &s_, &c_);
-        s.rotw[0] = s_; s.rotw[1] = c_;
-        sincos(TWO_PI_FL * dt_d / 1.0, &s_, &c_);
-        s.rotd[0] = s_; s.rotd[1] = c_;
+        if constexpr (SEAS) {
+            const double dt_d = (1e-9 * (double)step) / 86400.0;
+            double s_, c_;
+            sincos(TWO_PI_FL * dt_d / 7.0, &s_, &c_);
+            s.rotw[0] = s_; s.rotw[1] = c_;
+            sincos(TWO_PI_FL * dt_d / 1.0, &s_, &c_);
+            s.rotd[0] = s_; s.rotd[1] = c_;
+        }
         LSState& ls = s.ls;
         ls.ix = 0; ls.ig = 1; ls.ip = 2; ls.ixt = 3; ls.igt = 4; ls.ipp = 5;
         ls.iters = 0; ls.nevals = 0; ls.resetB = 1; ls.hn = 0; ls.hhead = 0;
@@ -1077,7 +1106,7 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
         plane[((size_t)(n / U) * G + own) * U + (n % U)] = (yv - fl) / y_scale;
     }
     // ---- per-lane start phases: weekly angle at the lane's first point, daily angle at its first table phase ----
-    {
+    if constexpr (SEAS) {
         const long long d0 = a.ds[off];
         const int i0 = gl * chunk;
         const double tw = (1e-9 * (double)(d0 + (long long)(i0 - 2) * step)) / 86400.0;     // two points before the chunk
@@ -1123,11 +1152,11 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
         int j0 = 0;
 #pragma unroll 1
         for (int q = 0; q < S; ++q) j0 += s.bidx[q] < i0 ? 1 : 0;
-        reinterpret_cast<int*>(&s.vec[1][0] + 6 * G)[gl] = j0;
+        reinterpret_cast<int*>(&s.vec[1][0] + (SEAS ? 6 * G : 0))[gl] = j0;
     }
     // ---- initial point: Prophet.{linear,logistic}_growth_init + stan_init ----
     {
-        const int P = S + GK + 3;
+        const int P = S + gkx<SEAS>() + 3;
         const double y0 = (load_y(a.y, a.y_dtype, off) - fl) / y_scale;
         const double y1 = (load_y(a.y, a.y_dtype, off + i1max) - fl) / y_scale;
         const double t1v = (double)(a.ds[off + i1max] - start) / dts;
@@ -1157,8 +1186,8 @@ __device__ __noinline__ bool g_fetch(GState<G>& s, const FitArgs& a, double* pla
 }
 
 // write the model record of the group's series (Stan's unconstrained optimum -> k, m, sigma_obs, delta, beta)
-template <int G>
-__device__ __noinline__ void g_write_record(GState<G>& s, const FitArgs& a, const int status, const int gl, const unsigned gm) {
+template <int G, bool SEAS>
+__device__ __noinline__ void g_write_record(GState<G, SEAS>& s, const FitArgs& a, const int status, const int gl, const unsigned gm) {
     const int sidx = s.series, S = s.S, ncp = s.ncp;
     const double* x = s.vec[s.ls.ix];
     double* pr = a.params + (size_t)sidx * a.pstride;
@@ -1178,14 +1207,14 @@ __device__ __noinline__ void g_write_record(GState<G>& s, const FitArgs& a, cons
             v = (c < S && ncp > 0) ? x[2 + c] : 0.0;
         } else {
             const int b = q - 3 - a.smax;
-            v = b < GK ? x[3 + S + b] : 0.0;
+            v = b < gkx<SEAS>() ? x[3 + S + b] : 0.0;
         }
         pr[q] = v;
     }
     if (a.theta_in) {
         const double* g = s.vec[s.ls.ig];
         double* go = a.grad_out + (size_t)sidx * a.pstride;
-        const int P = S + GK + 3;
+        const int P = S + gkx<SEAS>() + 3;
 #pragma unroll 1
         for (int q = gl; q < a.pstride; q += G) go[q] = q < P ? g[q] : 0.0;
     }
@@ -1205,29 +1234,36 @@ __device__ __noinline__ void g_write_record(GState<G>& s, const FitArgs& a, cons
 // ---------------------------------------------------------------------------------------
 // the kernel: one warp per CTA, 32 / G series in flight per warp, persistent over the class's work queue
 // ---------------------------------------------------------------------------------------
-template <int G, bool LOGI, bool MULT>
+template <int G, bool LOGI, bool MULT, bool SEAS>
 #ifndef PB200_GRP_BLOCKS
 // resident one-warp CTAs per SM the G = 8 register budget is set for.  8 -> 215 registers; 9 -> 168 registers with spills in
 // g_post_accept: 405 vs 376 ms per 50k-series step on the same box (r2l), whether 8 or 9 CTAs are actually resident (the
 // shared-memory footprint allows 9 either way: occupancy is not what limits this kernel)
 #define PB200_GRP_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(32, G == 8 ? PB200_GRP_BLOCKS : 16) fit_group_kernel(const FitArgs a) {
+#ifndef PB200_GRP_PLAIN_BLOCKS
+// ... and for the class without seasonality, whose time IS inversely proportional to the resident warps (r2s: 466 / 525 / 607 /
+// 806 ms per 500k short series at 8 / 7 / 6 / 4 CTAs per SM): short point loops, the latency of the serial code dominates
+#define PB200_GRP_PLAIN_BLOCKS 14
+#endif
+__global__ void __launch_bounds__(32, G != 8 ? 16 : (SEAS ? PB200_GRP_BLOCKS : PB200_GRP_PLAIN_BLOCKS)) fit_group_kernel(const FitArgs a) {
     static_assert(G == 8 || G == 16 || G == 32, "lanes per series");
-    static_assert(6 * G * 8 + G * 4 <= 5 * GPPAD * 8, "LanePhase hand-over through vec[1..5]");
+    static_assert(SEAS || !MULT, "without seasonality the additive form is the model");
+    static_assert((SEAS ? 6 * G * 8 : 0) + G * 4 <= 5 * GState<G, SEAS>::PPAD * 8, "LanePhase hand-over through vec[1..5]");
     constexpr int NSER = 32 / G;
     const int lane = threadIdx.x & 31, gi = lane / G, gl = lane % G;
     const unsigned gm = G == 32 ? FULL : (((1u << G) - 1u) << (gi * G));
-    GState<G>& s = gstate<G>(gi);
+    GState<G, SEAS>& s = gstate<G, SEAS>(gi);
     const size_t slot = (size_t)blockIdx.x * NSER + gi;
     double* const plane = reinterpret_cast<double*>(a.planes) + slot * (size_t)a.nseas_stride;
     double* const hist = plane + (a.nseas_stride - GHIST);
     double* const trace_base = a.trace;
-    const double tau = a.o.tau, rtau = a.o.rtau, inv_seas2 = a.o.inv_seas2;
+    // (the all-zero column of the class without seasonality has prior scale 1: fbprophet's make_all_seasonality_features)
+    const double tau = a.o.tau, rtau = a.o.rtau, inv_seas2 = SEAS ? a.o.inv_seas2 : 1.0;
     if (gl == 0) { s.state = ST_IDLE; s.series = -1; }
-    if (lane == 0) gopts<G>() = a.o;
+    if (lane == 0) gopts<G, SEAS>() = a.o;
     __syncwarp();
-    const FitOptsDev& opt = gopts<G>();
+    const FitOptsDev& opt = gopts<G, SEAS>();
     const double init_alpha = a.o.init_alpha;
     const int trace_cap = a.trace_cap;
     bool exhausted = false;
@@ -1237,15 +1273,17 @@ __global__ void __launch_bounds__(32, G == 8 ? PB200_GRP_BLOCKS : 16) fit_group_
     for (;;) {
         // ---- idle groups take the next series of the queue ----
         if (s.state == ST_IDLE && !exhausted) {
-            if (g_fetch<G, LOGI>(s, a, plane, gl, gm)) {
-                lp.wph = reinterpret_cast<const double2*>(&s.vec[1][0])[gl];
-                lp.dph = reinterpret_cast<const double2*>(&s.vec[1][0])[G + gl];
-                lp.wend = reinterpret_cast<const double2*>(&s.vec[1][0])[2 * G + gl];
-                lp.j0 = reinterpret_cast<const int*>(&s.vec[1][0] + 6 * G)[gl];
+            if (g_fetch<G, LOGI, SEAS>(s, a, plane, gl, gm)) {
+                if constexpr (SEAS) {
+                    lp.wph = reinterpret_cast<const double2*>(&s.vec[1][0])[gl];
+                    lp.dph = reinterpret_cast<const double2*>(&s.vec[1][0])[G + gl];
+                    lp.wend = reinterpret_cast<const double2*>(&s.vec[1][0])[2 * G + gl];
+                }
+                lp.j0 = reinterpret_cast<const int*>(&s.vec[1][0] + (SEAS ? 6 * G : 0))[gl];
                 int st = ST_FIRST;
                 if (a.theta_in) st = ST_OBJ;
                 else if (s.st0 == PB200_ST_CONST_LINEAR) {
-                    g_write_record<G>(s, a, PB200_ST_CONST_LINEAR, gl, gm);
+                    g_write_record<G, SEAS>(s, a, PB200_ST_CONST_LINEAR, gl, gm);
                     st = ST_IDLE;
                 }
                 __syncwarp(gm);
@@ -1265,16 +1303,16 @@ __global__ void __launch_bounds__(32, G == 8 ? PB200_GRP_BLOCKS : 16) fit_group_
         // ---- one objective + gradient evaluation per active group ----
         const bool first = state == ST_FIRST || state == ST_OBJ;
         const int ixv = first ? s.ls.ix : s.ls.ixt, igv = first ? s.ls.ig : s.ls.igt;
-        const int P = s.S + GK + 3;
+        const int P = s.S + gkx<SEAS>() + 3;
         if (active) {
-            g_eval_setup<G, LOGI>(s, s.vec[ixv], gl, gm);
+            g_eval_setup<G, LOGI, SEAS>(s, s.vec[ixv], gl, gm);
             if (gl == 0) s.ls.nevals += 1;
         }
         __syncwarp();
-        g_point_pass<G, LOGI, MULT, grp_u(G)>(s, plane, active, gl, lane, gm, lp);
+        g_point_pass<G, LOGI, MULT, SEAS, grp_u(G)>(s, plane, active, gl, lane, gm, lp);
         __syncwarp();
         int err = 0;
-        if (active) err = g_eval_finalize<G, LOGI>(s, s.vec[ixv], s.vec[igv], gl, gm, tau, rtau, inv_seas2, first ? &s.ls.fk : &s.ls.ft);
+        if (active) err = g_eval_finalize<G, LOGI, SEAS>(s, s.vec[ixv], s.vec[igv], gl, gm, tau, rtau, inv_seas2, first ? &s.ls.fk : &s.ls.ft);
         __syncwarp();
         // ---- the optimiser's reaction (BFGSMinimizer::step split at its evaluations) ----
         int act = -1, status = PB200_ST_SUCCESS;
@@ -1290,7 +1328,7 @@ __global__ void __launch_bounds__(32, G == 8 ? PB200_GRP_BLOCKS : 16) fit_group_
                 act = ACT_FAIL + 1;                                  // -> ls_begin below
             }
         } else if (state == ST_SEARCH) {
-            act = g_ls_step<G>(s, gl, gm, P, err);
+            act = g_ls_step<G, SEAS>(s, gl, gm, P, err);
         }
         __syncwarp();
         if (act == ACT_FAIL) {
@@ -1306,7 +1344,7 @@ __global__ void __launch_bounds__(32, G == 8 ? PB200_GRP_BLOCKS : 16) fit_group_
         __syncwarp();
         if (act == ACT_ACCEPT) {
             double* tr = trace_base ? trace_base + (size_t)s.series * trace_cap * 4 : nullptr;
-            status = g_post_accept<G>(s, hist, gl, gm, P, opt, tr, trace_cap);
+            status = g_post_accept<G, SEAS>(s, hist, gl, gm, P, opt, tr, trace_cap);
             if (status != PB200_ST_SUCCESS) done = true;
             else {
                 if (gl == 0) { s.ls.iters += 1; s.ls.resetB = 0; }
@@ -1315,10 +1353,10 @@ __global__ void __launch_bounds__(32, G == 8 ? PB200_GRP_BLOCKS : 16) fit_group_
             }
         }
         __syncwarp();
-        if (act == ACT_FAIL + 1) g_ls_begin<G>(s, gl, gm, P, init_alpha);
+        if (act == ACT_FAIL + 1) g_ls_begin<G, SEAS>(s, gl, gm, P, init_alpha);
         __syncwarp();
         if (done) {
-            g_write_record<G>(s, a, status, gl, gm);
+            g_write_record<G, SEAS>(s, a, status, gl, gm);
             if (gl == 0) s.state = ST_IDLE;
             __syncwarp(gm);
         }

@@ -12,6 +12,6 @@ PB200_DECL(0) PB200_DECL(1) PB200_DECL(2) PB200_DECL(3) PB200_DECL(4) PB200_DECL
 
 namespace pb200 {
 // grouped-lanes day-table kernel (fit_group_inst.cu): g = lanes per series (8 | 16)
-cudaError_t launch_fit_group(int g, int logi, int mult, const FitArgs& a, int grid, cudaStream_t st, int* occ);
+cudaError_t launch_fit_group(int g, int logi, int mult, int seas, const FitArgs& a, int grid, cudaStream_t st, int* occ);
 size_t fit_group_plane_doubles(int tmax, int g);      // global workspace per series slot (y pairs + L-BFGS history)
 }  // namespace pb200

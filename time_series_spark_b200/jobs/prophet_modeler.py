@@ -188,6 +188,7 @@ class ProphetModeler:
         """Header-less CSV ``dim_id,timestamp,quantity`` under hive dirs ``series_id=<int>/``
         (reference :102-116; fixture tests/fixtures/model-input).  Returns columns
         series_id, dim_id, ds, y."""
+        pdist.size_host_pools()             # pyarrow threads = this rank's share of the lease, not os.cpu_count()
         path = self.config["io"]["input"]
         part = pads.partitioning(pa.schema([("series_id", pa.int32())]), flavor="hive")
         names = [f.name for f in MODEL_INPUT_SCHEMA if f.name != "series_id"]

@@ -179,6 +179,7 @@ class ProphetScorer:
         self.config = config
 
     def read_model_dataframe(self, spark=None) -> Frame:
+        pdist.size_host_pools()             # pyarrow threads = this rank's share of the lease, not os.cpu_count()
         dset = pads.dataset(self.config["io"]["models"], format="parquet")
         return Frame(dset.to_table())
 
