@@ -100,6 +100,66 @@ def test_gpu_pack_matches_host_pack():
     assert np.array_equal(h.y, g.y.cpu().numpy())
 
 
+def _same_pack(h, g):
+    assert np.array_equal(h.series_id, g.series_id) and np.array_equal(h.dim_id, g.dim_id)
+    assert np.array_equal(h.offsets, g.offsets) and np.array_equal(h.last_ds, g.last_ds)
+    assert np.array_equal(h.n_rows_in, g.n_rows_in)
+    assert np.array_equal(h.ds, g.ds.cpu().numpy()) and np.array_equal(h.y, g.y.cpu().numpy())
+    assert h.y.dtype == g.y.cpu().numpy().dtype
+
+
+@pytest.mark.parametrize("case", ["chunked_seconds_negative_ids", "already_sorted", "float_y_with_nan", "bigger_than_a_slot",
+                                  "int64_columns"])
+def test_gpu_pack_upload_paths(case):
+    """The column upload of pack_groups_cuda (Arrow chunks -> pinned ring -> HBM, key and unit conversion on the device,
+    sort skipped for ordered input) against the host pack on the shapes it has to survive."""
+    import pyarrow as pa
+    from time_series_spark_b200 import pack
+    rng = np.random.RandomState(8)
+    if case == "chunked_seconds_negative_ids":
+        parts = []
+        for c in range(7):                                        # 7 chunks of uneven size, one of them empty
+            n = [0, 1, 513, 4000, 37, 2048, 900][c]
+            parts.append(pa.table({"series_id": pa.array(rng.randint(-3, 4, n).astype(np.int32)),
+                                   "dim_id": pa.array(rng.randint(-40, 40, n).astype(np.int32)),
+                                   "ds": pa.array(rng.randint(0, 3000, n).astype(np.int64) * 900, pa.int64()).cast(pa.timestamp("s")),
+                                   "y": pa.array(rng.randint(1, 99, n).astype(np.int32))}))
+        tbl = pa.concat_tables(parts)
+        assert tbl["ds"].num_chunks >= 6
+    elif case == "already_sorted":
+        n = 30000
+        sid = np.repeat(np.arange(30, dtype=np.int32), 1000)
+        did = np.tile(np.repeat(np.arange(10, dtype=np.int32), 100), 30)
+        ds = np.tile(np.arange(100, dtype=np.int64) * 900 * 10**9, 300)
+        tbl = pa.table({"series_id": sid, "dim_id": did, "ds": pa.array(ds).cast(pa.timestamp("ns")),
+                        "y": pa.array(rng.randint(1, 99, n).astype(np.int32))})
+    elif case == "float_y_with_nan":
+        n = 5000
+        y = rng.rand(n) * 100
+        y[rng.rand(n) < 0.03] = np.nan
+        tbl = pa.table({"series_id": pa.array(rng.randint(0, 3, n).astype(np.int32)), "dim_id": pa.array(rng.randint(0, 9, n).astype(np.int32)),
+                        "ds": pa.array(rng.randint(0, 900, n).astype(np.int64) * 60 * 10**9).cast(pa.timestamp("ns")),
+                        "y": pa.array(y, pa.float64(), mask=rng.rand(n) < 0.01)})
+    elif case == "bigger_than_a_slot":
+        old = pack._SLOT_BYTES
+        pack._SLOT_BYTES, pack._slots = 4096, {}                   # 512 int64 per slot: every column wraps the ring many times
+        try:
+            n = 9001
+            tbl = pa.table({"series_id": pa.array(rng.randint(0, 5, n).astype(np.int32)), "dim_id": pa.array(rng.randint(0, 50, n).astype(np.int32)),
+                            "ds": pa.array(rng.randint(0, 4000, n).astype(np.int64) * 10**9).cast(pa.timestamp("ns")),
+                            "y": pa.array(rng.randint(1, 999, n).astype(np.int32))})
+            _same_pack(pack.pack_groups(tbl, pin=False), pack.pack_groups_cuda(tbl))
+        finally:
+            pack._SLOT_BYTES, pack._slots = old, {}
+        return
+    else:
+        n = 4000
+        tbl = pa.table({"series_id": pa.array(rng.randint(0, 5, n).astype(np.int64)), "dim_id": pa.array(rng.randint(0, 50, n).astype(np.int64)),
+                        "ds": pa.array(rng.randint(0, 4000, n).astype(np.int64) * 10**9),             # plain int64 ns
+                        "y": pa.array(rng.randint(1, 999, n).astype(np.int64))})
+    _same_pack(pack.pack_groups(tbl, pin=False), pack.pack_groups_cuda(tbl))
+
+
 def test_make_future_device_matches_host(gpu_ctx):
     """pb200_make_future_device = Prophet.make_future_dataframe(include_history=False) for a fixed-width frequency:
     last + (1..periods) * freq, the grid batched.make_future builds on the host (and pandas date_range in test_boundary)."""

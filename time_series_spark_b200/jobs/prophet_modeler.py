@@ -94,6 +94,8 @@ class _ModelTimeSeriesOp:
         import torch
         torch.cuda.set_device(ctx.device)
         pk = pack_groups_cuda(table, device=f"cuda:{ctx.device}")
+        torch.cuda.synchronize()
+        t_pack = time.time()
         rank, ws, _ = pdist.world()
         if ws > 1 and not getattr(self, "rank_local_input", False):
             # the table holds EVERY group (the caller did not read rank-locally): this rank fits its contiguous,
@@ -116,6 +118,7 @@ class _ModelTimeSeriesOp:
             raise ValueError("Dataframe has less than 2 non-NaN rows." + _who(short))
         fitted = batched.fit_batch_device(ctx, opts, pk.ds.contiguous(), pk.y.contiguous(), pk.offsets,
                                           float(floor), float(cap_multiplier)).to_host()
+        t_fit = time.time()
         status = fitted.meta_i32[:, 4]
         if np.any(status == L.ST_CAP_LE_FLOOR):
             raise ValueError("cap must be greater than floor (which defaults to 0)." + _who(status == L.ST_CAP_LE_FLOOR))
@@ -137,6 +140,8 @@ class _ModelTimeSeriesOp:
         })
         if not ok.all():
             out = out.filter(pa.array(ok))
+        # wall time per stage of the last call (tools/e2e_scaling.py reports them): upload + group + sort, GPU fit + D2H, encode
+        self.last_timings = {"pack_s": t_pack - execution_time, "fit_s": t_fit - t_pack, "encode_s": time.time() - t_fit}
         print(f"Output df {out.num_rows} models trained in {time.time() - execution_time}")
         return out
 

@@ -64,7 +64,9 @@ def run(d):
         t3 = time.perf_counter()
         stages = {"read_s": t1 - t0, "fit_s": t2 - t1, "write_s": t3 - t2, "total_s": t3 - t0,
                   "rows_read": df.count(), "models": models.count()}
-    vals = torch.tensor([stages[k] for k in ("read_s", "fit_s", "write_s", "total_s")], dtype=torch.float64, device="cuda")
+        stages.update({"op_" + k: v for k, v in getattr(op, "last_timings", {}).items()})
+    keys = ("read_s", "fit_s", "write_s", "total_s", "op_pack_s", "op_fit_s", "op_encode_s")
+    vals = torch.tensor([stages.get(k, 0.0) for k in keys], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([stages["rows_read"], stages["models"]], dtype=torch.int64, device="cuda")
     if ws > 1:
         import torch.distributed as dist
@@ -74,9 +76,10 @@ def run(d):
     else:
         allc = [cnt]
     if rank == 0:
-        r, f, w, t = [float(x) for x in vals.tolist()]
+        r, f, w, t, opk, ofi, oen = [float(x) for x in vals.tolist()]
         print(json.dumps({"ranks": ws, "rank_local_input": bool(getattr(job, "rank_local_input", False)),
                           "read_s": r, "fit_s": f, "write_s": w, "total_s": t,
+                          "fit_stage": {"pack_upload_group_sort_s": opk, "gpu_fit_and_d2h_s": ofi, "encode_records_s": oen},
                           "rows_read_by_rank": [int(c[0]) for c in allc], "models_by_rank": [int(c[1]) for c in allc]}))
     if ws > 1:
         import torch.distributed as dist
