@@ -489,6 +489,7 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
             if (c->tab_on && LC_NT[lc] == 32) pa.tab_lc_mask |= 1 << lc;
         pa.grp_g = grp_g;
         pa.grp_plain = (c->plain_grp && grp_g > 0) ? 1 : 0;
+        { static const char* e = getenv("PB200_QKEY_CV"); pa.cv_weight = e ? atof(e) : 2.0; }
         pa.newton_only = (opts->algorithm == PB200_ALG_NEWTON && !d_theta_in) ? 1 : 0;
         pa.nq_count = nq;
         pa.nq_items = nq + 2;
@@ -854,7 +855,9 @@ PB200_API int pb200_predict_device(pb200_ctx* c, const pb200_options* opts, cons
     a.trend = nullptr;
     a.yhat_int = d_yhat_int;
     {
-        dim3 grid((unsigned)n_models, (unsigned)std::min((horizon + 255) / 256, 64));
+        // one CTA per (model, 1024 future points): the per-model prologue (parameters, the serial gamma recurrence) is paid
+        // once for config #5's 672 periods instead of three times
+        dim3 grid((unsigned)n_models, (unsigned)std::min((horizon + 1023) / 1024, 64));
         pb200::predict_kernel<<<grid, 256, 0, c->stream>>>(a);
         CK(cudaGetLastError());
         c->launches++;

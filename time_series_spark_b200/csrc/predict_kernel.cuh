@@ -36,13 +36,32 @@ struct PredictArgs {
 
 constexpr double PI_FL = 3.141592653589793;
 
+// sin / cos of a Fourier argument.  With t in days since 1970 the arguments are 1e4 ... 1e6 radians (daily harmonics of a
+// 2022 date: 2 pi 4 19000 = 4.8e5), beyond the 1.05e5 up to which the library's sincos reduces with its short
+// Cody-Waite path: every daily and most weekly terms took the Payne-Hanek slow path, and 14 of those per point made
+// predict_kernel ~7 % of its HBM roofline.  Reduce here instead: 2 pi in three parts, the first two
+// of 32 significant bits, so that k C1 and k C2 are exact for k < 2^21 and r = x - k 2 pi is good to 4.4e-16 absolute
+// (checked in exact rational arithmetic over +-8e6); then the library call sees |r| <= pi.  The argument x itself stays
+// the ROUNDED double numpy forms -- the reduction is of that value, not of the mathematical angle.
+__device__ __forceinline__ void sincos_reduced(const double x, double* s, double* c) {
+    const double k = rint(x * 0.15915494309189535);
+    if (fabs(k) < 2097152.0) {
+        double r = fma(-k, 6.2831853069365025, x);             // 0x1.921fb544p+2 : exact
+        r = fma(-k, 2.4308402025215864e-10, r);                // 0x1.0b4611a6p-32
+        r = fma(-k, 8.089064995183803e-21, r);                 // 0x1.3198a2e037073p-67
+        sincos(r, s, c);
+    } else {
+        sincos(x, s, c);
+    }
+}
+
 // Prophet.fourier_series evaluated exactly as numpy does: fun(2.0 * (i + 1) * np.pi * t / period)
 __device__ __forceinline__ double seas_dot(const double tau, const double period, const int order, const double* beta) {
     double acc = 0.0;
     for (int i = 0; i < order; ++i) {
         const double arg = (2.0 * (double)(i + 1)) * PI_FL * tau / period;
         double s, c;
-        sincos(arg, &s, &c);
+        sincos_reduced(arg, &s, &c);
         acc = fma(s, beta[2 * i], acc);
         acc = fma(c, beta[2 * i + 1], acc);
     }
