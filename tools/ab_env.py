@@ -8,10 +8,13 @@ from time_series_spark_b200 import synth, batched, _lib as L
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 specs = sys.argv[3:] or ["base:"]
-KNOWN = ("PB200_NO_TAB", "PB200_GROUP", "PB200_GRP_PAD", "PB200_PLAIN_GROUP", "PB200_QKEY_CV", "PB200_LC0_MAX", "PB200_LC1_MAX")
+KNOWN = ("PB200_NO_TAB", "PB200_GROUP", "PB200_GRP_PAD", "PB200_PLAIN_GROUP", "PB200_LC0_MAX", "PB200_LC1_MAX")
 cfg = os.environ.get("AB_CONFIG", "c3")          # c3 (50k x 1440 shape) or c4 (short ragged series, no seasonality)
 b = synth.config4(n=n) if cfg == "c4" else synth.config3(n=n); opts = batched.make_options()
 mask = 0 if cfg == "c4" else 6
+if os.environ.get("AB_STEP_MIN"):                       # same values on another regular grid (e.g. 30 min: table period 48)
+    T0 = int(b.offsets[1] - b.offsets[0])
+    b.ds[:] = np.tile(b.ds[0] + int(os.environ["AB_STEP_MIN"]) * 60 * 10**9 * np.arange(T0, dtype=np.int64), n)
 ds = torch.from_numpy(b.ds).cuda(); y = torch.from_numpy(b.y).cuda()
 res = {}
 for spec in specs:
