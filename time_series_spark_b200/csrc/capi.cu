@@ -520,7 +520,7 @@ static int fit_impl(pb200_ctx* c, FitWs& w, const pb200_options* opts, const int
             g.on = false;
             g.grouped = false;
             if (lc_n[lc] == 0) continue;
-            const bool plain_grp = reg == 3 && mask == 0 && grp_g > 0;   // grouped kernel's class without seasonality
+            const bool plain_grp = reg == 3 && mask == 0 && grp_g > 0 && c->plain_grp;   // grouped kernel's class without seasonality
             if (reg && mask == 0 && !plain_grp) continue;                // no Fourier features: nothing to regenerate
             if (reg >= 2 && ((mask != 6 && !plain_grp) || LC_NT[lc] != 32 || !c->tab_on)) continue;   // seasonal-table variants
             auto impossible = [&](int bit, int sw) { return (sw == 0 && (mask & bit)) || (sw == 1 && !(mask & bit)); };
