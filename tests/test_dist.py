@@ -64,3 +64,26 @@ def test_gather_rows_gloo_world2():
     assert sid == np.arange(10).repeat(3).tolist()
     assert yh == (np.arange(10).repeat(3) * 0.5).tolist()
     assert len(ds) == 30
+
+
+def test_usable_cores_and_pool_sizing(monkeypatch):
+    """Host threads = CPU affinity capped by the cgroup quota (not os.cpu_count()); each rank of a node sizes its pyarrow
+    pools to its share of them (a 2-rank modeler run parsed its CSV slower than one rank before this: DESIGN 5)."""
+    import pyarrow as pa
+    uc = pdist.usable_cores()
+    assert 1 <= uc["usable"] <= uc["affinity"] <= uc["logical"]
+    if uc["cgroup_quota"] is not None:
+        assert uc["usable"] <= max(1, int(uc["cgroup_quota"] + 0.5))
+    before = (pa.cpu_count(), pa.io_thread_count())
+    try:
+        monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+        assert pdist.size_host_pools() == uc["usable"] == pa.cpu_count()
+        monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+        n2 = pdist.size_host_pools()
+        assert n2 == max(1, uc["usable"] // 2) == pa.cpu_count()
+        assert 2 <= pa.io_thread_count() <= 8
+        monkeypatch.setenv("LOCAL_WORLD_SIZE", str(4 * uc["usable"]))        # more ranks than threads: one each
+        assert pdist.size_host_pools() == 1
+    finally:
+        pa.set_cpu_count(before[0])
+        pa.set_io_thread_count(before[1])
