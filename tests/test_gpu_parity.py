@@ -450,6 +450,79 @@ def test_day_table_other_kernels_objective_and_gradient(warp_ctx_tab32, warp_ctx
     _check_table_objective(warp_ctx_tab32 if kernel == "tab32" else warp_ctx_g16, warp_ctx_no_tab, case, "logistic_multiplicative")
 
 
+@pytest.mark.parametrize("kernel", ["default_small_batch", "grouped_g8", "one_warp_rotation"])
+def test_y_dtypes_give_identical_fits(gpu_ctx, warp_ctx, warp_ctx_no_tab, kernel):
+    """The C ABI takes y as int32, float32 or float64 (prophet_b200.h y_dtype).  Integer counts are exact in all three, so
+    the three calls must give the same bits on every kernel family; and a genuinely fractional float64 y is held to the
+    oracle's objective / gradient like the integer fixtures."""
+    ctx = {"default_small_batch": gpu_ctx, "grouped_g8": warp_ctx, "one_warp_rotation": warp_ctx_no_tab}[kernel]
+    b = synth.config3(n=8)
+    opts, oopts = batched.make_options(), po.ProphetOptions()
+    outs = []
+    for dt in (np.int32, np.float32, np.float64):
+        y = b.y.astype(dt)
+        assert np.array_equal(y.astype(np.float64), b.y.astype(np.float64))           # exactly representable
+        fb = batched.fit_batch_host(ctx, opts, b.ds, y, b.offsets, 0.0, 1.1)
+        outs.append(fb)
+        assert np.all(fb.meta_i32[:, 4] >= 0)
+    for fb in outs[1:]:
+        assert np.array_equal(fb.params, outs[0].params) and np.array_equal(fb.meta_i32, outs[0].meta_i32)
+        assert np.array_equal(fb.meta_f64, outs[0].meta_f64)
+    # fractional float64 values: objective and gradient against the oracle at random points
+    rng = np.random.RandomState(2)
+    yf = b.y.astype(np.float64) * (1.0 + 1e-3 * rng.rand(b.y.size)) + 0.37
+    lay = L.get_layout(opts)
+    th, preps = [], []
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        p = po.prepare(b.ds[a:e], yf[a:e], 0.0, yf[a:e].max() * 1.1, oopts)
+        t = po.initial_theta(p) + 0.05 * rng.randn(p.S + p.K + 3)
+        row = np.zeros(lay.pstride)
+        row[:t.size] = t
+        th.append(row)
+        preps.append((p, t))
+    f, g, mi = batched.objective_host(ctx, opts, b.ds, yf, b.offsets, 0.0, 1.1, np.array(th))
+    for i, (p, t) in enumerate(preps):
+        err, fo, go = po.neg_logp_grad(t, p)
+        assert err == 0 and mi[i, 4] == 0
+        assert abs(f[i] - fo) <= 1e-10 * max(1.0, abs(fo)), (kernel, i, f[i], fo)
+        assert np.max(np.abs(g[i, :t.size] - go)) <= 1e-8 * max(1.0, np.max(np.abs(go))), (kernel, i)
+
+
+@pytest.mark.parametrize("kernel", ["default_small_batch", "grouped_g8"])
+def test_explicit_cap_array_and_nonzero_floor(gpu_ctx, warp_ctx, kernel):
+    """pb200_fit_* take either cap_multiplier (the reference UDF: cap = max(y) * multiplier, prophet_modeler.py:59) or a cap
+    per series; and the reference's floor is a config value, not always 0 (prophet_modeler.py:57-58).  The explicit caps
+    max(y) * 1.1 must reproduce the multiplier path bit for bit, and the objective with a non-zero floor must match the oracle."""
+    ctx = gpu_ctx if kernel == "default_small_batch" else warp_ctx
+    b = synth.config3(n=8)
+    opts, oopts = batched.make_options(), po.ProphetOptions()
+    floor = 12.5
+    caps = np.array([b.y[b.offsets[i]:b.offsets[i + 1]].astype(np.float64).max() * 1.1 for i in range(b.n)])
+    f1 = batched.fit_batch_host(ctx, opts, b.ds, b.y, b.offsets, floor, 1.1)
+    f2 = batched.fit_batch_host(ctx, opts, b.ds, b.y, b.offsets, floor, 0.0, cap=caps)
+    assert np.array_equal(f1.params, f2.params) and np.array_equal(f1.meta_i32, f2.meta_i32)
+    assert np.array_equal(f1.meta_f64, f2.meta_f64) and np.array_equal(f1.meta_f64[:, 2], caps)
+    assert np.all(f1.meta_f64[:, 1] == floor)
+    rng = np.random.RandomState(4)
+    lay = L.get_layout(opts)
+    th, preps = [], []
+    for i in range(b.n):
+        a, e = b.offsets[i], b.offsets[i + 1]
+        p = po.prepare(b.ds[a:e], b.y[a:e].astype(np.float64), floor, caps[i], oopts)
+        t = po.initial_theta(p) + 0.05 * rng.randn(p.S + p.K + 3)
+        row = np.zeros(lay.pstride)
+        row[:t.size] = t
+        th.append(row)
+        preps.append((p, t))
+    f, g, mi = batched.objective_host(ctx, opts, b.ds, b.y, b.offsets, floor, 1.1, np.array(th))
+    for i, (p, t) in enumerate(preps):
+        err, fo, go = po.neg_logp_grad(t, p)
+        assert err == 0 and mi[i, 4] == 0
+        assert abs(f[i] - fo) <= 1e-10 * max(1.0, abs(fo)), (kernel, i, f[i], fo)
+        assert np.max(np.abs(g[i, :t.size] - go)) <= 1e-8 * max(1.0, np.max(np.abs(go))), (kernel, i)
+
+
 def _plain_cases():
     c3 = synth.config3(n=8)
     tiny = synth.config4(n=12, tmin=2, tmax=13)                     # 2 .. 13 points: fewer points than lanes, ncp < 25
