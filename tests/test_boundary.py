@@ -217,6 +217,42 @@ def test_written_forecast_timestamps_look_like_sparks(tmp_path):
     assert _re.fullmatch(r"\d{4}-\d\d-\d\dT\d\d:\d\d:\d\d\.\d{3}Z", lines[2].replace('"', "").split(",")[4])
 
 
+def test_big_forecast_frame_is_written_as_parallel_part_files(tmp_path, monkeypatch):
+    """A frame above _ROWS_PER_PART rows goes out as several part files written concurrently, timestamps formatted
+    through their dictionary: the concatenated rows must be exactly what the single-file path writes."""
+    import pyarrow.compute as pc
+    from time_series_spark_b200.jobs import prophet_scorer as ps
+    rng = np.random.RandomState(1)
+    n_models, H = 37, 53
+    grid = 1546300805 * 10**9 + 900 * 10**9 * np.arange(H, dtype=np.int64)
+    tbl = pa.table({"series_id": pa.array(np.repeat(np.arange(n_models, dtype=np.int32) // 5, H)),
+                    "dim_id": pa.array(np.repeat(np.arange(n_models, dtype=np.int32) % 5, H)),
+                    "ds": pa.array(np.tile(grid, n_models)).cast(pa.timestamp("ns")),
+                    "yhat": pa.array(rng.randint(0, 10**6, n_models * H).astype(np.int32))})
+    cfg = lambda d: {"io": {"models": "unused", "forecasts": str(tmp_path / d)}, "forecast": {"periods": H, "frequency": "15min"}}
+    frame = ProphetScorer.convert_forecasts(Frame(tbl))
+    ProphetScorer(cfg("one")).write_forecasts(frame)
+    monkeypatch.setattr(ps, "_ROWS_PER_PART", 300)
+    ProphetScorer(cfg("many")).write_forecasts(frame)
+    one = open(tmp_path / "one" / "part-00000.csv").read().strip().split("\n")
+    parts = sorted(os.listdir(tmp_path / "many"))
+    assert len(parts) == -(-n_models * H // 300) and parts[0] == "part-00000-0000.csv"
+    many = []
+    for i, fn in enumerate(parts):
+        lines = open(tmp_path / "many" / fn).read().strip().split("\n")
+        assert lines[0] == one[0]                                   # every part file carries the header, as Spark's do
+        many += lines[1:]
+    assert many == one[1:] and len(many) == n_models * H
+    # the dictionary route == pc.strftime: few distinct values, all distinct values, chunked input, empty input
+    for arr in (tbl["ds"], pa.chunked_array([tbl["ds"].chunk(0).slice(0, 100), tbl["ds"].chunk(0).slice(100, 0), tbl["ds"].chunk(0).slice(100)]),
+                pa.array(np.sort(rng.randint(0, 2**40, 500)).astype(np.int64) * 1000).cast(pa.timestamp("ns")),
+                pa.array([], pa.timestamp("ns"))):
+        for fmt in ("%Y-%m-%d", "%Y-%m-%dT%H:%M:%SZ"):
+            src = pc.cast(arr, pa.timestamp("ms"), safe=False) if "T" in fmt else arr
+            got, want = ps._strftime_via_dictionary(src, fmt), pc.strftime(src, format=fmt)
+            assert got.to_pylist() == want.to_pylist() and got.type == pa.string()
+
+
 def test_rank_local_files_cover_the_input_once(tmp_path):
     """SURVEY 8e "rank r reads only its row range": the series_id= directories are cut into contiguous,
     byte-balanced ranges, one per rank; together they are the whole input, pairwise disjoint."""

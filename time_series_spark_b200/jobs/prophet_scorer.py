@@ -171,6 +171,28 @@ def extract_date(datetimestamp: datetime):
     return datetimestamp.date().strftime("%Y-%m-%d")
 
 
+_ROWS_PER_PART = 1 << 20
+
+
+def _strftime_via_dictionary(ts, fmt: str):
+    """``pc.strftime`` costs 0.5-0.9 us per VALUE (16 s for 8 M forecast rows, against 3 ms for the GPU to compute them), and a
+    forecast frame repeats few distinct timestamps -- every model's horizon is the same handful of grid points.  Format the
+    distinct values only and expand through the dictionary indices (a 20 ns per row memcpy).  Falls back to the direct call
+    when most values are distinct."""
+    chunks = ts.chunks if isinstance(ts, pa.ChunkedArray) else [ts]
+    out = []
+    for ch in chunks:
+        if len(ch) == 0:
+            out.append(pc.strftime(ch, format=fmt))
+            continue
+        enc = ch.dictionary_encode()
+        if len(enc.dictionary) * 4 > len(ch):
+            out.append(pc.strftime(ch, format=fmt))
+        else:
+            out.append(pa.DictionaryArray.from_arrays(enc.indices, pc.strftime(enc.dictionary, format=fmt)).cast(pa.string()))
+    return pa.chunked_array(out, pa.string()) if isinstance(ts, pa.ChunkedArray) else out[0]
+
+
 class ProphetScorer:
     """Forecast quantities using trained models (reference :114-165)."""
 
@@ -195,7 +217,7 @@ class ProphetScorer:
             pa.DictionaryArray.from_arrays(pa.array(np.zeros(n, np.int32)), pa.array([created_timestamp])).cast(pa.string()),
             "series_id": t["series_id"],
             "dim_id": t["dim_id"],
-            "forecast_date": pc.strftime(ds, format="%Y-%m-%d"),
+            "forecast_date": _strftime_via_dictionary(ds, "%Y-%m-%d"),
             "forecast_timestamp": ds,
             "forecast_quantity": t["yhat"],
         }
@@ -216,9 +238,21 @@ class ProphetScorer:
             # cast to milliseconds first (a timestamp[ns] column would print nine digits).
             i = t.column_names.index("forecast_timestamp")
             ms = pc.cast(t["forecast_timestamp"], pa.timestamp("ms"), safe=False)
-            t = t.set_column(i, "forecast_timestamp", pc.strftime(ms, format="%Y-%m-%dT%H:%M:%SZ"))
-        pacsv.write_csv(t, os.path.join(out, f"part-{rank:05d}.csv"),
-                        write_options=pacsv.WriteOptions(include_header=True, quoting_style="needed"))
+            t = t.set_column(i, "forecast_timestamp", _strftime_via_dictionary(ms, "%Y-%m-%dT%H:%M:%SZ"))
+        wo = pacsv.WriteOptions(include_header=True, quoting_style="needed")
+        n = t.num_rows
+        if n <= _ROWS_PER_PART:
+            pacsv.write_csv(t, os.path.join(out, f"part-{rank:05d}.csv"), write_options=wo)
+            return
+        # a big frame goes out as several part files written concurrently (Spark's output is a directory of part files
+        # too; pyarrow's CSV writer releases the GIL): config #5's 67 M rows are ~5 GB of text
+        from concurrent.futures import ThreadPoolExecutor
+        bounds = list(range(0, n, _ROWS_PER_PART)) + [n]
+        def write(k):
+            pacsv.write_csv(t.slice(bounds[k], bounds[k + 1] - bounds[k]),
+                            os.path.join(out, f"part-{rank:05d}-{k:04d}.csv"), write_options=wo)
+        with ThreadPoolExecutor(max_workers=max(1, pdist.size_host_pools())) as pool:
+            list(pool.map(write, range(len(bounds) - 1)))
 
     @staticmethod
     def score(spark_session, config):
