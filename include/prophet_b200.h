@@ -251,6 +251,26 @@ PB200_API int pb200_make_future_device(pb200_ctx* ctx, const int64_t* d_last_ds,
 
 PB200_API int pb200_synchronize(pb200_ctx* ctx);
 
+/*
+ * Forecast CSV rows formatted on the device: the row formatting of convert_forecasts + write_forecasts
+ * (src/jobs/prophet_scorer.py:131-150 -- extract_date per row :107-108, created_timestamp :134, Spark's CSV writer
+ * :147-150) for the standard frame
+ *     "created_timestamp",series_id,dim_id,"forecast_date","forecast_timestamp",forecast_quantity
+ * Two passes: row lengths, then -- given the exclusive scan of the lengths as byte offsets -- the bytes
+ * (d_out holds the sum of the lengths).  ds in [1970-01-01, 10000-01-01); created_timestamp at most 64 bytes.
+ * pb200_forecast_csv_row_host runs the same row formatter on the host for ONE row (tests; returns the row's
+ * length, out must hold 160 bytes).
+ */
+PB200_API int pb200_forecast_csv_lengths_device(pb200_ctx* ctx, const int32_t* d_series_id, const int32_t* d_dim_id,
+                                                const int32_t* d_quantity, int64_t n_rows, int32_t created_len,
+                                                int64_t* d_row_len);
+PB200_API int pb200_forecast_csv_rows_device(pb200_ctx* ctx, const int32_t* d_series_id, const int32_t* d_dim_id,
+                                             const int64_t* d_ds_ns, const int32_t* d_quantity, int64_t n_rows,
+                                             const char* h_created, int32_t created_len, const int64_t* d_row_off,
+                                             uint8_t* d_out);
+PB200_API int32_t pb200_forecast_csv_row_host(int32_t series_id, int32_t dim_id, int64_t ds_ns, int32_t quantity,
+                                              const char* created, int32_t created_len, char* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,7 +48,7 @@ EXPORTS = [
     "pb200_default_options", "pb200_get_layout", "pb200_create", "pb200_destroy", "pb200_last_error",
     "pb200_stream", "pb200_launch_count", "pb200_last_fit_variant_counts", "pb200_tab_chunk", "pb200_fit_device", "pb200_fit_host", "pb200_predict_device",
     "pb200_predict_host", "pb200_make_future_device", "pb200_synchronize", "pb200_objective_host",
-    "pb200_fit_trace_host",
+    "pb200_fit_trace_host", "pb200_forecast_csv_lengths_device", "pb200_forecast_csv_rows_device", "pb200_forecast_csv_row_host",
 ]
 
 _lib = None
@@ -100,6 +100,12 @@ def load() -> C.CDLL:
     lib.pb200_objective_host.restype = C.c_int
     lib.pb200_fit_trace_host.argtypes = [vp, OP, vp, vp, i32, vp, i64, dbl, dbl, vp, vp, vp, vp, vp, vp, i32]
     lib.pb200_fit_trace_host.restype = C.c_int
+    lib.pb200_forecast_csv_lengths_device.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    lib.pb200_forecast_csv_lengths_device.restype = C.c_int
+    lib.pb200_forecast_csv_rows_device.argtypes = [vp, vp, vp, vp, vp, i64, C.c_char_p, i32, vp, vp]
+    lib.pb200_forecast_csv_rows_device.restype = C.c_int
+    lib.pb200_forecast_csv_row_host.argtypes = [i32, i32, i64, i32, C.c_char_p, i32, C.c_char_p]
+    lib.pb200_forecast_csv_row_host.restype = i32
     lib.pb200_synchronize.argtypes = [vp]
     lib.pb200_synchronize.restype = C.c_int
     _lib = lib

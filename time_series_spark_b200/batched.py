@@ -208,6 +208,46 @@ def make_future_device(ctx: L.Context, last_ds_ns, periods: int, freq_ns: int):
     return out
 
 
+def forecast_csv_device(ctx: L.Context, series_id, dim_id, ds_ns, quantity, created: bytes):
+    """The CSV text of forecast rows, formatted on the GPU (pb200_forecast_csv_{lengths,rows}_device): int32 / int32 /
+    int64 ns / int32 CUDA tensors of equal length in, one uint8 CUDA tensor out (no header line).  Row format and the
+    supported timestamp range: include/prophet_b200.h."""
+    import torch
+    n = int(series_id.shape[0])
+    dev = series_id.device
+    if n == 0:
+        return torch.empty(0, dtype=torch.uint8, device=dev)
+    for t, dt in ((series_id, torch.int32), (dim_id, torch.int32), (ds_ns, torch.int64), (quantity, torch.int32)):
+        if t.dtype != dt or not t.is_contiguous() or int(t.shape[0]) != n or t.device != dev:
+            raise ValueError("forecast_csv_device wants contiguous int32 / int32 / int64 / int32 tensors of one length on one device")
+    lib = L.load()
+    lens = torch.empty(n, dtype=torch.int64, device=dev)
+    torch.cuda.current_stream(dev).synchronize()
+    L.check(lib.pb200_forecast_csv_lengths_device(ctx.handle, series_id.data_ptr(), dim_id.data_ptr(), quantity.data_ptr(), n,
+                                                  len(created), lens.data_ptr()), "pb200_forecast_csv_lengths_device")
+    ctx.synchronize()
+    ends = torch.cumsum(lens, 0)                      # the scan is plumbing (torch); the two passes over the rows are the kernels
+    total = int(ends[-1].item())
+    offs = ends - lens
+    out = torch.empty(total, dtype=torch.uint8, device=dev)
+    torch.cuda.current_stream(dev).synchronize()
+    L.check(lib.pb200_forecast_csv_rows_device(ctx.handle, series_id.data_ptr(), dim_id.data_ptr(), ds_ns.data_ptr(),
+                                               quantity.data_ptr(), n, created, len(created), offs.data_ptr(), out.data_ptr()),
+            "pb200_forecast_csv_rows_device")
+    ctx.synchronize()
+    return out
+
+
+def forecast_csv_row_host(series_id: int, dim_id: int, ds_ns: int, quantity: int, created: bytes) -> bytes:
+    """One row through the same formatter on the host (pb200_forecast_csv_row_host; tests)."""
+    import ctypes
+    buf = ctypes.create_string_buffer(160)
+    n = L.load().pb200_forecast_csv_row_host(int(series_id), int(dim_id), int(ds_ns), int(quantity), created, len(created), buf)
+    if n < 0:
+        raise ValueError("pb200_forecast_csv_row_host refused the row")
+    return buf.raw[:n]
+
+
 def predict_batch_host(ctx: L.Context, opts: L.Options, fitted: FittedBatch, future_ds: np.ndarray,
                        floor: np.ndarray, cap: np.ndarray, seed: int = 0, intervals: bool = True) -> ForecastBatch:
     """pb200_predict_host.  ``floor`` / ``cap`` per model as the scorer reads them back from

@@ -6,6 +6,7 @@
 #include "predict_kernel.cuh"
 #include "mc_kernel.cuh"
 #include "newton_kernel.cuh"
+#include "csv_kernel.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -925,6 +926,68 @@ PB200_API int pb200_predict_host(pb200_ctx* c, const pb200_options* opts, const 
     }
     CK(cudaStreamSynchronize(st));
     return PB200_OK;
+}
+
+// ---- forecast CSV rows formatted on the device (csv_kernel.cuh) ----
+static int csv_args(pb200::csv::CsvArgs& a, const int32_t* sid, const int32_t* did, const int64_t* ds, const int32_t* qty, int64_t n,
+                    const char* created, int32_t created_len) {
+    if (created_len < 0 || created_len > pb200::csv::MAX_CREATED) return fail(PB200_E_ARG, "created_timestamp longer than 64 bytes");
+    if (created_len && !created) return fail(PB200_E_ARG, "null pointer");
+    a.sid = sid; a.did = did; a.ds_ns = (const long long*)ds; a.qty = qty; a.n = n; a.created_len = created_len;
+    memset(a.created, 0, sizeof(a.created));
+    if (created_len) memcpy(a.created, created, (size_t)created_len);
+    a.row_len = nullptr; a.row_off = nullptr; a.out = nullptr;
+    return PB200_OK;
+}
+
+PB200_API int pb200_forecast_csv_lengths_device(pb200_ctx* c, const int32_t* d_series_id, const int32_t* d_dim_id,
+                                                const int32_t* d_quantity, int64_t n_rows, int32_t created_len,
+                                                int64_t* d_row_len) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    if (n_rows < 0) return fail(PB200_E_ARG, "sizes");
+    if (n_rows == 0) return PB200_OK;
+    if (!d_series_id || !d_dim_id || !d_quantity || !d_row_len) return fail(PB200_E_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    pb200::csv::CsvArgs a;
+    char pad[pb200::csv::MAX_CREATED] = {0};
+    int rc = csv_args(a, d_series_id, d_dim_id, nullptr, d_quantity, n_rows, pad, created_len);
+    if (rc) return rc;
+    a.row_len = (long long*)d_row_len;
+    const int grid = (int)std::min<int64_t>((n_rows + 255) / 256, (int64_t)c->sms * 16);
+    pb200::csv::csv_lengths_kernel<<<grid, 256, 0, c->stream>>>(a);
+    CK(cudaGetLastError());
+    c->launches++;
+    return PB200_OK;
+}
+
+PB200_API int pb200_forecast_csv_rows_device(pb200_ctx* c, const int32_t* d_series_id, const int32_t* d_dim_id,
+                                             const int64_t* d_ds_ns, const int32_t* d_quantity, int64_t n_rows,
+                                             const char* h_created, int32_t created_len, const int64_t* d_row_off,
+                                             uint8_t* d_out) {
+    if (!c) return fail(PB200_E_ARG, "ctx is null");
+    if (n_rows < 0) return fail(PB200_E_ARG, "sizes");
+    if (n_rows == 0) return PB200_OK;
+    if (!d_series_id || !d_dim_id || !d_ds_ns || !d_quantity || !d_row_off || !d_out) return fail(PB200_E_ARG, "null pointer");
+    CK(cudaSetDevice(c->device));
+    pb200::csv::CsvArgs a;
+    int rc = csv_args(a, d_series_id, d_dim_id, d_ds_ns, d_quantity, n_rows, h_created, created_len);
+    if (rc) return rc;
+    a.row_off = (const long long*)d_row_off;
+    a.out = d_out;
+    const int64_t warps = (n_rows + 31) / 32;
+    const int grid = (int)std::min<int64_t>((warps + 3) / 4, (int64_t)c->sms * 8);
+    pb200::csv::csv_rows_kernel<<<grid, 128, 0, c->stream>>>(a);
+    CK(cudaGetLastError());
+    c->launches++;
+    return PB200_OK;
+}
+
+PB200_API int32_t pb200_forecast_csv_row_host(int32_t series_id, int32_t dim_id, int64_t ds_ns, int32_t quantity,
+                                              const char* created, int32_t created_len, char* out) {
+    if (created_len < 0 || created_len > pb200::csv::MAX_CREATED || !out || (created_len && !created)) return -1;
+    char* e = pb200::csv::put_row(out, series_id, dim_id, ds_ns, quantity, created, created_len);
+    const int n = (int)(e - out);
+    return n == pb200::csv::row_len(series_id, dim_id, quantity, created_len) ? n : -1;
 }
 
 }  // extern "C"

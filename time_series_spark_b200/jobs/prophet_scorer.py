@@ -193,6 +193,88 @@ def _strftime_via_dictionary(ts, fmt: str):
     return pa.chunked_array(out, pa.string()) if isinstance(ts, pa.ChunkedArray) else out[0]
 
 
+_GPU_ROWS_PER_PART = 4 << 20
+_CSV_HEADER = b'"created_timestamp","series_id","dim_id","forecast_date","forecast_timestamp","forecast_quantity"\n'
+
+
+def _gpu_writer_refusal(output_df: Frame, big_only: bool):
+    """None if the frame can go through the GPU row formatter (csrc/csv_kernel.cuh), else the reason it cannot."""
+    src = getattr(output_df, "forecast_source", None)
+    if src is None:
+        return "not the direct result of convert_forecasts"
+    created, t = src
+    if output_df.table.column_names != ["created_timestamp", "series_id", "dim_id", "forecast_date", "forecast_timestamp",
+                                        "forecast_quantity"] or output_df.table.num_rows != t.num_rows:
+        return "columns other than the standard six (interval columns keep the Arrow writer)"
+    if big_only and t.num_rows <= _ROWS_PER_PART:
+        return "small frame"
+    if len(created.encode()) > 64:
+        return "created_timestamp longer than 64 bytes"
+    for c in ("series_id", "dim_id", "yhat"):
+        if not pa.types.is_integer(t[c].type) or t[c].null_count:
+            return f"column {c} is not a null-free integer column"
+    if not pa.types.is_timestamp(t["ds"].type) or t["ds"].null_count:
+        return "ds is not a null-free timestamp column"
+    if t.num_rows and pc.min(pc.cast(t["ds"], pa.int64())).as_py() < 0:
+        return "timestamps before 1970"
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return "no CUDA device"
+    except Exception:
+        return "no CUDA device"
+    return None
+
+
+def _write_forecasts_gpu(output_df: Frame, out: str, rank: int):
+    """Part files of at most _GPU_ROWS_PER_PART rows: columns up through pack's pinned ring, rows formatted by
+    pb200_forecast_csv_*_device, text back through two pinned buffers, file writes on a thread so that the GPU formats
+    part k + 1 while part k goes to disk.  Byte for byte the Arrow writer's output (tests/test_gpu_jobs.py)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from ..pack import _device_column
+    created, t = output_df.forecast_source
+    ctx = get_context()
+    torch.cuda.set_device(ctx.device)
+    dev = torch.device("cuda", ctx.device)
+    n = t.num_rows
+    unit = t["ds"].type.unit
+    mult = {"s": 10**9, "ms": 10**6, "us": 10**3, "ns": 1}[unit]
+    bounds = list(range(0, n, _GPU_ROWS_PER_PART)) + [n]
+    single = len(bounds) == 2
+    host = [None, None]
+    pending = [None, None]
+
+    def dump(path, buf, nbytes):
+        with open(path, "wb") as f:
+            f.write(_CSV_HEADER)
+            f.write(memoryview(buf.numpy())[:nbytes])
+
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        for k in range(len(bounds) - 1):
+            a, m = bounds[k], bounds[k + 1] - bounds[k]
+            sid = _device_column(t["series_id"].slice(a, m), pa.int32(), dev)
+            did = _device_column(t["dim_id"].slice(a, m), pa.int32(), dev)
+            qty = _device_column(t["yhat"].slice(a, m), pa.int32(), dev)
+            ds = _device_column(t["ds"].slice(a, m), pa.int64(), dev)
+            if mult != 1:
+                ds *= mult
+            text = batched.forecast_csv_device(ctx, sid, did, ds, qty, created.encode())
+            nbytes = int(text.numel())
+            b = k & 1
+            if pending[b] is not None:
+                pending[b].result()                                    # the buffer's previous part is on disk
+            if host[b] is None or host[b].numel() < nbytes:
+                host[b] = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            host[b][:nbytes].copy_(text)
+            torch.cuda.current_stream(dev).synchronize()
+            name = f"part-{rank:05d}.csv" if single else f"part-{rank:05d}-{k:04d}.csv"
+            pending[b] = pool.submit(dump, os.path.join(out, name), host[b], nbytes)
+        for p in pending:
+            if p is not None:
+                p.result()
+
+
 class ProphetScorer:
     """Forecast quantities using trained models (reference :114-165)."""
 
@@ -224,7 +306,10 @@ class ProphetScorer:
         for extra in ("yhat_lower", "yhat_upper"):
             if extra in t.column_names:
                 cols[extra] = t[extra]
-        return Frame(pa.table(cols))
+        out = Frame(pa.table(cols))
+        # what the frame was made from: lets write_forecasts format the rows on the GPU instead of from these columns
+        out.forecast_source = (created_timestamp, t)
+        return out
 
     def write_forecasts(self, output_df: Frame):
         """CSV with header, mode='overwrite' (reference :147-150); a directory of part files."""
@@ -232,6 +317,15 @@ class ProphetScorer:
         rank = pdist.world()[0]
         pdist.prepare_output_dir(out)
         t = output_df.table
+        writer = (self.config.get("forecast", {}) or {}).get("writer", "auto")      # auto | gpu | arrow
+        if writer not in ("auto", "gpu", "arrow"):
+            raise ValueError("forecast.writer must be 'auto', 'gpu' or 'arrow'")
+        if writer != "arrow":
+            why = _gpu_writer_refusal(output_df, big_only=(writer == "auto"))
+            if why is None:
+                return _write_forecasts_gpu(output_df, out, rank)
+            if writer == "gpu":
+                raise ValueError("forecast.writer = 'gpu' cannot write this frame: " + why)
         if "forecast_timestamp" in t.column_names and pa.types.is_timestamp(t["forecast_timestamp"].type):
             # Spark's CSV writer prints timestamps as yyyy-MM-dd'T'HH:mm:ss.SSSXXX by default, e.g.
             # 2019-01-01T00:00:05.000Z.  Arrow's %S prints the fraction at the column's unit, so the column is
