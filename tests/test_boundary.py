@@ -253,6 +253,39 @@ def test_big_forecast_frame_is_written_as_parallel_part_files(tmp_path, monkeypa
             assert got.to_pylist() == want.to_pylist() and got.type == pa.string()
 
 
+def test_gpu_writer_eligibility_rules(tmp_path):
+    """Which frames write_forecasts hands to the GPU row formatter (forecast.writer = auto) -- decided on the host."""
+    from time_series_spark_b200.jobs import prophet_scorer as ps
+    H = 8
+    mk = lambda ds0: pa.table({"series_id": pa.array(np.zeros(H, np.int32)), "dim_id": pa.array(np.arange(H, dtype=np.int32)),
+                               "ds": pa.array(ds0 + 900 * 10**9 * np.arange(H, dtype=np.int64)).cast(pa.timestamp("ns")),
+                               "yhat": pa.array(np.arange(H, dtype=np.int32))})
+    f = ProphetScorer.convert_forecasts(Frame(mk(1_650_000_000 * 10**9)))
+    assert f.forecast_source[1].num_rows == H
+    assert ps._gpu_writer_refusal(f, big_only=True) == "small frame"
+    why = ps._gpu_writer_refusal(f, big_only=False)
+    try:
+        import torch
+        cuda = torch.cuda.is_available()
+    except Exception:
+        cuda = False
+    assert why == (None if cuda else "no CUDA device")
+    assert "convert_forecasts" in ps._gpu_writer_refusal(Frame(f.table), big_only=False)                  # provenance unknown
+    old = ProphetScorer.convert_forecasts(Frame(mk(-5 * 86400 * 10**9)))
+    assert ps._gpu_writer_refusal(old, big_only=False) == "timestamps before 1970"
+    iv = mk(0).append_column("yhat_lower", pa.array(np.zeros(H))).append_column("yhat_upper", pa.array(np.ones(H)))
+    assert "standard six" in ps._gpu_writer_refusal(ProphetScorer.convert_forecasts(Frame(iv)), big_only=False)
+    with pytest.raises(ValueError):
+        ProphetScorer({"io": {"forecasts": str(tmp_path / "x")}, "forecast": {"writer": "fpga"}}).write_forecasts(f)
+    if not cuda:                                        # forcing the GPU route without a device fails loudly, no silent fallback
+        with pytest.raises(ValueError):
+            ProphetScorer({"io": {"forecasts": str(tmp_path / "y")}, "forecast": {"writer": "gpu"}}).write_forecasts(f)
+    # the one-row host formatter (the code the kernel runs) against a hand-written row
+    from time_series_spark_b200 import batched
+    assert batched.forecast_csv_row_host(12, -3, 1_546_300_805_123_456_789, 42, b"2019-01-01T00:00:00+00:00") == \
+        b'"2019-01-01T00:00:00+00:00",12,-3,"2019-01-01","2019-01-01T00:00:05.123Z",42\n'
+
+
 def test_rank_local_files_cover_the_input_once(tmp_path):
     """SURVEY 8e "rank r reads only its row range": the series_id= directories are cut into contiguous,
     byte-balanced ranges, one per rank; together they are the whole input, pairwise disjoint."""
