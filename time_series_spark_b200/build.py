@@ -49,7 +49,9 @@ def _sources_digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    stamp = os.path.join(OBJ, "digest.txt")
+    # the stamp lives next to the library, not in _build/: the objects stay behind when a snapshot of the tree is sent to
+    # a GPU box (.gpurunignore) but the library travels, and without its stamp every test session there recompiled it
+    stamp = LIB + ".digest"
     digest = _sources_digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
